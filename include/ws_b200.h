@@ -1,0 +1,241 @@
+/*
+ * ws_b200.h -- C ABI of the B200-native watershed engine.
+ *
+ * This is the drop-in boundary for the hot path of smups/rustronomy-watershed
+ * v0.4.1 (all citations are into the reference's src/lib.rs).  The reference is
+ * a pure-Rust crate with no FFI of its own; the entry points below are what a
+ * `extern "C"` block in a shim crate binds so that `TransformBuilder`,
+ * `Watershed::{transform, transform_with_hook, transform_to_list,
+ * transform_history}` and `WatershedUtils::find_local_minima` keep their
+ * signatures while the work runs as hand-written sm_100a CUDA
+ * (INTEGRATION.md shows that shim).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; images are u8, axis 0 = row ("x" in the
+ *     reference), strides are in ELEMENTS and may be negative (ArrayView2);
+ *   - seeds are `[n][2]` uint64 = (row, col), the repacked `&[(usize, usize)]`;
+ *   - labels ("colours") are uint64 like the reference's usize, 0 = UNCOLOURED
+ *     (lib.rs:138), colour of seed i = i + 1 (lib.rs:1360-1367);
+ *   - every function returns a ws_status; nothing throws, nothing aborts.  The
+ *     reference's run-time failures are panics (e.g. out-of-bounds seed,
+ *     lib.rs:1366); the shim turns a non-zero status back into a panic;
+ *   - there is NO CPU fallback: without a CUDA device ws_ctx_create fails;
+ *   - a ws_ctx is used by one thread at a time (the shim keeps one per thread);
+ *     per-level hooks run on the calling thread, in level order.
+ */
+#ifndef WS_B200_H
+#define WS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WS_ABI_VERSION 1
+
+/* lib.rs:138-141 */
+#define WS_UNCOLOURED 0u
+#define WS_NORMAL_MAX 254u
+#define WS_ALWAYS_FILL 0u
+#define WS_NEVER_FILL 255u
+
+typedef enum ws_status {
+  WS_OK = 0,
+  WS_ERR_INVALID_ARG = 1,
+  WS_ERR_MAX_TOO_HIGH = 2, /* BuildErr::MaxToHigh, lib.rs:1000-1001, 1052 */
+  WS_ERR_MAX_TOO_LOW = 3,  /* BuildErr::MaxToLow,  lib.rs:1002-1003, 1053 */
+  WS_ERR_SEED_OOB = 4,     /* the reference panics: lib.rs:1366 / 1676     */
+  WS_ERR_NO_DEVICE = 5,
+  WS_ERR_CUDA = 6,
+  WS_ERR_OOM = 7,
+  WS_ERR_TOO_LARGE = 8,    /* image or seed list beyond the engine's limits */
+  WS_ERR_HOP_OVERFLOW = 9, /* a flood path longer than 2^24 - 2 steps in one level */
+  WS_ERR_INTERNAL = 10
+} ws_status;
+
+typedef enum ws_kind {
+  WS_SEGMENTING = 0, /* SegmentingWatershed, lib.rs:1609-1848 */
+  WS_MERGING = 1     /* MergingWatershed,    lib.rs:1297-1562 */
+} ws_kind;
+
+/* The fields of TransformBuilder that reach the hot path (lib.rs:917-919).    */
+typedef struct ws_config {
+  uint8_t kind;            /* ws_kind                                          */
+  uint8_t max_water_level; /* 1..=254, default NORMAL_MAX (lib.rs:942)         */
+  uint8_t edge_correction; /* enable_edge_correction(), lib.rs:958-961         */
+  uint8_t reserved;        /* must be 0                                        */
+} ws_config;
+
+/* ArrayView2<u8>: base pointer of element (0,0), shape, strides in elements.  */
+typedef struct ws_image {
+  const uint8_t *data;
+  size_t rows, cols;
+  ptrdiff_t row_stride, col_stride;
+} ws_image;
+
+typedef struct ws_ctx ws_ctx; /* device, streams, workspaces                   */
+
+/* ---- context ------------------------------------------------------------ */
+ws_status ws_ctx_create(int device, ws_ctx **out);
+void ws_ctx_destroy(ws_ctx *ctx);
+/* Message of the last failure on this ctx ("" if none); valid until the next call. */
+const char *ws_last_error(const ws_ctx *ctx);
+const char *ws_status_str(ws_status s);
+int ws_abi_version(void);
+/* Frees memory handed out by the library (ws_find_local_minima).              */
+void ws_free(void *p);
+
+/* ---- TransformBuilder::build_segmenting / build_merging (lib.rs:998-1046) -- */
+/* Only the validation is left to do: 1 <= max_water_level <= 254.             */
+ws_status ws_config_validate(const ws_config *cfg);
+/* Shape of every label image the transform returns: the input shape, or two
+ * more in each axis with edge correction (lib.rs:1330-1337; the padding is NOT
+ * removed from hook contexts and results, and seeds are NOT shifted, 1365-1367). */
+ws_status ws_output_shape(const ws_config *cfg, size_t rows, size_t cols,
+                          size_t *out_rows, size_t *out_cols);
+
+/* ---- WatershedUtils::find_local_minima (lib.rs:1178-1197) ---------------- */
+/* Interior pixels strictly GREATER than all 8 neighbours (the code, not its
+ * doc comment), no plateau resolution, in row-major order.  *out_rc is a
+ * library-owned `[n][2]` array of (row, col); release it with ws_free.        */
+ws_status ws_find_local_minima(ws_ctx *ctx, const ws_image *img,
+                               uint64_t **out_rc, size_t *out_n);
+
+/* ---- Watershed::transform (lib.rs:1208) ---------------------------------- */
+/* Segmenting (lib.rs:1810-1822): label image after the last water level.  The
+ * reference indexes element 0 of the hook results and panics ("no output?");
+ * the intended value -- the colours at max_water_level -- is returned here.
+ * Ties between differently coloured neighbours (random in the reference,
+ * lib.rs:250-253) resolve to the FIRST coloured neighbour in the reference's
+ * order down, right, left, up (lib.rs:190, `col0` of line 245).
+ * Merging (lib.rs:1524-1536): interior 123, border 0, seeds ignored.
+ * out_labels: out_rows * out_cols uint64, C order.                            */
+ws_status ws_transform(ws_ctx *ctx, const ws_config *cfg, const ws_image *img,
+                       const uint64_t *seeds_rc, size_t nseeds,
+                       uint64_t *out_labels);
+
+/* ---- Watershed::transform_history (lib.rs:1233; 1538-1549; 1824-1835) ---- */
+/* One snapshot per water level 0..=max_water_level, in order.
+ * out_levels: max+1 bytes.  out_labels: (max+1) * out_rows * out_cols uint64.
+ * Merging labels: the representative of a merged lake is its smallest seed
+ * colour; the reference's choice (region[0], lib.rs:539) depends on an
+ * unspecified sort order, so parity is "equal up to a renumbering per level". */
+ws_status ws_transform_history(ws_ctx *ctx, const ws_config *cfg,
+                               const ws_image *img, const uint64_t *seeds_rc,
+                               size_t nseeds, uint8_t *out_levels,
+                               uint64_t *out_labels);
+
+/* ---- Watershed::transform_to_list (lib.rs:1220; 1551-1561; 1837-1847) ----- */
+/* Per level the histogram of the label image exactly as find_lake_sizes
+ * builds it (lib.rs:629-635): length out_rows*out_cols + 1, index 0 counts the
+ * uncoloured pixels.  out_sizes: (max+1) * (out_rows*out_cols + 1) uint64.    */
+ws_status ws_transform_to_list(ws_ctx *ctx, const ws_config *cfg,
+                               const ws_image *img, const uint64_t *seeds_rc,
+                               size_t nseeds, uint8_t *out_levels,
+                               uint64_t *out_sizes);
+
+/* ---- Watershed::transform_with_hook (lib.rs:1214; 1328-1522; 1638-1808) --- */
+/* HookCtx (lib.rs:844-850).  `image` is the (padded) input, `colours` the
+ * label image after this level's merge, both C order and host-resident for the
+ * duration of the call; `seeds` is `[nseeds][3]` = (colour, row, col).        */
+typedef struct ws_hook_ctx {
+  uint8_t water_level;
+  uint8_t max_water_level;
+  const uint8_t *image;
+  const uint64_t *colours;
+  size_t rows, cols;
+  const uint64_t *seeds;
+  size_t nseeds;
+} ws_hook_ctx;
+typedef void (*ws_level_hook)(void *user, const ws_hook_ctx *hctx);
+/* Calls `hook` once per level on the calling thread, in level order.          */
+ws_status ws_transform_with_hook(ws_ctx *ctx, const ws_config *cfg,
+                                 const ws_image *img, const uint64_t *seeds_rc,
+                                 size_t nseeds, ws_level_hook hook, void *user);
+
+/* ---- compact results (extensions; same computation, smaller outputs) ------ */
+/* Per level: number of lakes (distinct non-zero labels) and of uncoloured
+ * pixels -- what a caller derives from transform_to_list, without the
+ * (rows*cols+1)-long rows.  out_*: max+1 uint64 each (either may be NULL).    */
+ws_status ws_transform_lake_counts(ws_ctx *ctx, const ws_config *cfg,
+                                   const ws_image *img, const uint64_t *seeds_rc,
+                                   size_t nseeds, uint64_t *out_lake_counts,
+                                   uint64_t *out_uncoloured);
+/* Final segmenting labels as uint32 plus, per pixel, the water level at which
+ * it was coloured (255 = never): snapshot L == (level <= L ? label : 0).      */
+ws_status ws_transform_compact(ws_ctx *ctx, const ws_config *cfg,
+                               const ws_image *img, const uint64_t *seeds_rc,
+                               size_t nseeds, uint32_t *out_labels,
+                               uint8_t *out_level);
+
+/* ---- batches of equally shaped slices (one launch set for all of them) ---- */
+/* imgs: n_img contiguous C-order slices.  seeds_rc: the slices' seed lists
+ * back to back, seed_offsets[n_img+1] delimiting them.  Outputs are optional:
+ * out_labels [n_img][out_rows*out_cols] (segmenting final labels),
+ * out_lake_counts [n_img][max+1] (lakes per level; the merging statistic).    */
+ws_status ws_transform_batch(ws_ctx *ctx, const ws_config *cfg,
+                             const uint8_t *imgs, size_t n_img, size_t rows,
+                             size_t cols, const uint64_t *seeds_rc,
+                             const uint64_t *seed_offsets, uint64_t *out_labels,
+                             uint64_t *out_lake_counts);
+/* find_local_minima over a batch; *out_rc as in ws_find_local_minima,
+ * out_offsets[n_img+1] is caller-allocated.                                   */
+ws_status ws_find_local_minima_batch(ws_ctx *ctx, const uint8_t *imgs,
+                                     size_t n_img, size_t rows, size_t cols,
+                                     uint64_t **out_rc, uint64_t *out_offsets);
+
+/* ---- device-resident pipeline (inputs and results stay in HBM) ------------ */
+/* For callers that already hold the data on the GPU (a torch tensor, a decoded
+ * FITS cube) and for timing the kernels without PCIe.  All pointers below are
+ * device pointers on the ctx's device; work is enqueued on ws_ctx_stream().   */
+typedef struct ws_plan ws_plan;
+void *ws_ctx_stream(ws_ctx *ctx); /* cudaStream_t */
+ws_status ws_ctx_synchronize(ws_ctx *ctx);
+/* Workspace for n_img slices of rows x cols (the shape actually flooded).     */
+ws_status ws_plan_create(ws_ctx *ctx, size_t n_img, size_t rows, size_t cols,
+                         ws_plan **out);
+void ws_plan_destroy(ws_plan *plan);
+/* Seeds of every slice: d_seeds_rc `[cap][2]` uint32 receives (row, col) in
+ * row-major order per slice, d_seed_off[n_img+1] uint32 the offsets.
+ * *out_total (host) is the number found; WS_ERR_TOO_LARGE if it exceeds cap.  */
+ws_status ws_plan_find_local_minima(ws_plan *plan, const uint8_t *d_imgs,
+                                    uint32_t *d_seeds_rc, size_t cap,
+                                    uint32_t *d_seed_off, size_t *out_total);
+/* Flood all levels and resolve labels.  kind = WS_MERGING also runs the
+ * per-level union-find and fills the lake counts.                             */
+ws_status ws_plan_run(ws_plan *plan, const ws_config *cfg, const uint8_t *d_imgs,
+                      const uint32_t *d_seeds_rc, const uint32_t *d_seed_off,
+                      size_t nseeds_total);
+/* Results of the last ws_plan_run (owned by the plan, valid until the next run):
+ * labels  [n_img][rows*cols] uint32, segmenting labels (0 = uncoloured);
+ * levels  [n_img][rows*cols] uint8, level of colouring (255 = never);
+ * counts  [n_img][256] uint32, lakes at each level (merging runs only).       */
+const uint32_t *ws_plan_labels(const ws_plan *plan);
+const uint8_t *ws_plan_levels(const ws_plan *plan);
+const uint32_t *ws_plan_lake_counts(const ws_plan *plan);
+/* Diagnostic: arrival times [n_img][rows*cols] uint32 = (level << 24) | hop, hop being
+ * the index of the flood pass (lib.rs:1394 'colouring_loop) inside the level;
+ * seeds 0, never-coloured pixels >= 0xFF000000.                               */
+const uint32_t *ws_plan_arrival_times(const ws_plan *plan);
+/* Label image of slice `i` at water level `level` as uint64 into d_out
+ * (rows*cols).  Merging snapshots need the run to have been WS_MERGING.       */
+ws_status ws_plan_snapshot(ws_plan *plan, ws_kind kind, size_t i, uint8_t level,
+                           uint64_t *d_out);
+/* Counters of the last run: [0] flood sweeps, [1] tile activations,
+ * [2] pointer-jumping rounds, [3] merge edges, [4] kernels launched.          */
+ws_status ws_plan_stats(ws_plan *plan, uint64_t out[8]);
+
+/* ---- plain device-memory helpers for callers without a CUDA runtime of their own ---- */
+ws_status ws_dev_malloc(ws_ctx *ctx, size_t bytes, void **out);
+ws_status ws_dev_free(ws_ctx *ctx, void *d_ptr);
+/* Copies ordered after the work already enqueued on the ctx stream; both return
+ * after the copy has completed.                                               */
+ws_status ws_memcpy_h2d(ws_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+ws_status ws_memcpy_d2h(ws_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WS_B200_H */

@@ -1,0 +1,260 @@
+"""ctypes binding of libws_b200.so (the C ABI of include/ws_b200.h).
+
+There is no fallback of any kind: if the library is missing, or no sm_100
+device is present, creating a Context raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libws_b200.so")
+
+WS_OK = 0
+STATUS_NAMES = {
+    0: "WS_OK", 1: "WS_ERR_INVALID_ARG", 2: "WS_ERR_MAX_TOO_HIGH", 3: "WS_ERR_MAX_TOO_LOW",
+    4: "WS_ERR_SEED_OOB", 5: "WS_ERR_NO_DEVICE", 6: "WS_ERR_CUDA", 7: "WS_ERR_OOM",
+    8: "WS_ERR_TOO_LARGE", 9: "WS_ERR_HOP_OVERFLOW", 10: "WS_ERR_INTERNAL",
+}
+WS_ERR_MAX_TOO_HIGH, WS_ERR_MAX_TOO_LOW, WS_ERR_SEED_OOB, WS_ERR_NO_DEVICE = 2, 3, 4, 5
+WS_SEGMENTING, WS_MERGING = 0, 1
+
+
+class WsConfig(C.Structure):
+    _fields_ = [("kind", C.c_uint8), ("max_water_level", C.c_uint8),
+                ("edge_correction", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+class WsImage(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_size_t), ("cols", C.c_size_t),
+                ("row_stride", C.c_ssize_t), ("col_stride", C.c_ssize_t)]
+
+
+class WsHookCtx(C.Structure):
+    _fields_ = [("water_level", C.c_uint8), ("max_water_level", C.c_uint8),
+                ("image", C.c_void_p), ("colours", C.c_void_p),
+                ("rows", C.c_size_t), ("cols", C.c_size_t),
+                ("seeds", C.c_void_p), ("nseeds", C.c_size_t)]
+
+
+HOOK_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(WsHookCtx))
+
+# name -> (restype, argtypes); every symbol include/ws_b200.h declares
+_P = C.c_void_p
+SIGNATURES = {
+    "ws_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "ws_ctx_destroy": (None, [_P]),
+    "ws_last_error": (C.c_char_p, [_P]),
+    "ws_status_str": (C.c_char_p, [C.c_int]),
+    "ws_abi_version": (C.c_int, []),
+    "ws_free": (None, [_P]),
+    "ws_config_validate": (C.c_int, [C.POINTER(WsConfig)]),
+    "ws_output_shape": (C.c_int, [C.POINTER(WsConfig), C.c_size_t, C.c_size_t,
+                                  C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "ws_find_local_minima": (C.c_int, [_P, C.POINTER(WsImage), C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "ws_transform": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t, _P]),
+    "ws_transform_history": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t, _P, _P]),
+    "ws_transform_to_list": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t, _P, _P]),
+    "ws_transform_with_hook": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t,
+                                         HOOK_FN, _P]),
+    "ws_transform_lake_counts": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t, _P, _P]),
+    "ws_transform_compact": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t, _P, _P]),
+    "ws_transform_batch": (C.c_int, [_P, C.POINTER(WsConfig), _P, C.c_size_t, C.c_size_t, C.c_size_t,
+                                     _P, _P, _P, _P]),
+    "ws_find_local_minima_batch": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(_P), _P]),
+    "ws_ctx_stream": (_P, [_P]),
+    "ws_ctx_synchronize": (C.c_int, [_P]),
+    "ws_plan_create": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(_P)]),
+    "ws_plan_destroy": (None, [_P]),
+    "ws_plan_find_local_minima": (C.c_int, [_P, _P, _P, C.c_size_t, _P, C.POINTER(C.c_size_t)]),
+    "ws_plan_run": (C.c_int, [_P, C.POINTER(WsConfig), _P, _P, _P, C.c_size_t]),
+    "ws_plan_labels": (_P, [_P]),
+    "ws_plan_levels": (_P, [_P]),
+    "ws_plan_lake_counts": (_P, [_P]),
+    "ws_plan_arrival_times": (_P, [_P]),
+    "ws_plan_snapshot": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_uint8, _P]),
+    "ws_dev_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "ws_dev_free": (C.c_int, [_P, _P]),
+    "ws_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "ws_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "ws_plan_stats": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8)]),
+}
+
+_lib = None
+
+
+class WatershedError(RuntimeError):
+    """A non-zero ws_status.  The Rust shim turns these into panics."""
+
+    def __init__(self, status: int, message: str = ""):
+        self.status = status
+        name = STATUS_NAMES.get(status, str(status))
+        super().__init__(f"{name}: {message}" if message else name)
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the CUDA library and bind every declared symbol (fails loudly)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(f"{p} not found: build it with __graft_entry__.build() "
+                          "(the engine has no CPU fallback)")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def make_config(kind: int, max_water_level: int, edge_correction: bool) -> WsConfig:
+    return WsConfig(kind, max_water_level, 1 if edge_correction else 0, 0)
+
+
+def image_view(img: np.ndarray) -> WsImage:
+    """ArrayView2<u8> of a numpy array, strides preserved (no copy)."""
+    if img.dtype != np.uint8 or img.ndim != 2:
+        raise TypeError("image must be a 2-D uint8 array")
+    return WsImage(img.ctypes.data, img.shape[0], img.shape[1], img.strides[0], img.strides[1])
+
+
+def seeds_array(seeds) -> np.ndarray:
+    """&[(usize, usize)] -> C-contiguous [n][2] uint64."""
+    a = np.asarray(seeds)
+    if a.size == 0:
+        return np.zeros((0, 2), dtype=np.uint64)
+    if np.issubdtype(a.dtype, np.signedinteger) and (a < 0).any():
+        raise OverflowError("seed coordinates are usize: negative values are not representable")
+    return np.ascontiguousarray(a.reshape(-1, 2), dtype=np.uint64)
+
+
+class Context:
+    """Owns a ws_ctx (device, streams, workspaces).  Single-threaded use."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _P()
+        st = self.lib.ws_ctx_create(device, C.byref(h))
+        if st != WS_OK:
+            raise WatershedError(st, self.lib.ws_status_str(st).decode())
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ws_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, st: int):
+        if st != WS_OK:
+            msg = self.lib.ws_last_error(self.handle)
+            raise WatershedError(st, (msg or b"").decode() or self.lib.ws_status_str(st).decode())
+
+    # -- plain device memory (for callers that do not bring torch / cuda-python) --
+    def dev_malloc(self, nbytes: int) -> int:
+        out = _P()
+        self.check(self.lib.ws_dev_malloc(self.handle, nbytes, C.byref(out)))
+        return int(out.value)
+
+    def dev_free(self, ptr: int):
+        self.check(self.lib.ws_dev_free(self.handle, ptr))
+
+    def h2d(self, d_ptr: int, arr: np.ndarray):
+        a = np.ascontiguousarray(arr)
+        self.check(self.lib.ws_memcpy_h2d(self.handle, d_ptr, a.ctypes.data, a.nbytes))
+
+    def d2h(self, d_ptr: int, shape, dtype) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        self.check(self.lib.ws_memcpy_d2h(self.handle, out.ctypes.data, d_ptr, out.nbytes))
+        return out
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of the compute stream as an integer (torch.cuda.ExternalStream)."""
+        return int(self.lib.ws_ctx_stream(self.handle) or 0)
+
+    def synchronize(self):
+        self.check(self.lib.ws_ctx_synchronize(self.handle))
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """One lazily created Context per device (what the Rust shim keeps per thread)."""
+    ctx = _default_ctx.get(device)
+    if ctx is None or ctx.handle is None:
+        ctx = Context(device)
+        _default_ctx[device] = ctx
+    return ctx
+
+
+class Plan:
+    """Device-resident pipeline (ws_plan_*): pointers are CUDA device pointers (ints)."""
+
+    def __init__(self, ctx: Context, n_img: int, rows: int, cols: int):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.n_img, self.rows, self.cols = n_img, rows, cols
+        h = _P()
+        ctx.check(self.lib.ws_plan_create(ctx.handle, n_img, rows, cols, C.byref(h)))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None) and self.ctx.handle:
+            self.lib.ws_plan_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def find_local_minima(self, d_imgs: int, d_seeds_rc: int, cap: int, d_seed_off: int) -> int:
+        total = C.c_size_t(0)
+        self.ctx.check(self.lib.ws_plan_find_local_minima(self.handle, d_imgs, d_seeds_rc, cap, d_seed_off,
+                                                          C.byref(total)))
+        return int(total.value)
+
+    def run(self, kind: int, max_water_level: int, d_imgs: int, d_seeds_rc: int, d_seed_off: int, nseeds: int):
+        cfg = make_config(kind, max_water_level, False)
+        self.ctx.check(self.lib.ws_plan_run(self.handle, C.byref(cfg), d_imgs, d_seeds_rc, d_seed_off, nseeds))
+
+    @property
+    def labels_ptr(self) -> int:
+        return int(self.lib.ws_plan_labels(self.handle) or 0)
+
+    @property
+    def levels_ptr(self) -> int:
+        return int(self.lib.ws_plan_levels(self.handle) or 0)
+
+    @property
+    def arrival_times_ptr(self) -> int:
+        return int(self.lib.ws_plan_arrival_times(self.handle) or 0)
+
+    @property
+    def lake_counts_ptr(self) -> int:
+        return int(self.lib.ws_plan_lake_counts(self.handle) or 0)
+
+    def snapshot(self, kind: int, i: int, level: int, d_out: int):
+        self.ctx.check(self.lib.ws_plan_snapshot(self.handle, kind, i, level, d_out))
+
+    def stats(self) -> dict:
+        arr = (C.c_uint64 * 8)()
+        self.ctx.check(self.lib.ws_plan_stats(self.handle, C.byref(arr)))
+        return {"flood_sweeps": arr[0], "tile_activations": arr[1], "jump_rounds": arr[2],
+                "merge_edges": arr[3], "kernel_launches": arr[4]}

@@ -1,0 +1,49 @@
+// common.cuh -- shared definitions of the sm_100a watershed kernels.
+//
+// Arrival-time encoding: every pixel carries one u32
+//     T = (level << 24) | hop
+// = the water level at which the reference's loop colours it (lib.rs:1379 /
+// 1689) and the index of the synchronous flood pass inside that level
+// (lib.rs:1394 / 1704 'colouring_loop).  Seeds hold T = 0, pixels that are
+// never coloured hold T >= T_INF.  The reference's nested loops are the unique
+// fixed point of
+//     T(p) = max(A(p), 1 + min over 4-neighbours q of T(q)),   A(p) = (img[p] << 24) | 1
+// for interior pixels with img[p] <= max_water_level (A(p) = T_INF otherwise),
+// so any relaxation order reaches the same result.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ws {
+
+constexpr uint32_t T_INF = 0xFF000000u;     // level 255, hop 0: "never coloured"
+constexpr uint32_t HOP_MASK = 0x00FFFFFFu;
+constexpr uint32_t LAB_RESOLVED = 0x80000000u;  // lab word holds a final label, not a pixel index
+constexpr uint32_t LAB_MASK = 0x7FFFFFFFu;
+
+// Flood tile: TILE_W x TILE_H pixels per CTA, each thread owns ROWS_PER_THREAD
+// consecutive rows of one column.
+constexpr int TILE_W = 64;
+constexpr int TILE_H = 32;
+constexpr int ROWS_PER_THREAD = 8;
+constexpr int FLOOD_THREADS = TILE_W * TILE_H / ROWS_PER_THREAD;  // 256
+constexpr int SM_W = TILE_W + 2;
+constexpr int SM_H = TILE_H + 2;
+
+struct ImageDims {
+  int n_img;      // slices in the batch
+  int rows, cols; // per slice
+  int tiles_x, tiles_y;
+  __host__ __device__ size_t px_per_img() const { return (size_t)rows * (size_t)cols; }
+  __host__ __device__ size_t px_total() const { return px_per_img() * (size_t)n_img; }
+  __host__ __device__ int tiles_per_img() const { return tiles_x * tiles_y; }
+  __host__ __device__ int tiles_total() const { return tiles_per_img() * n_img; }
+};
+
+__device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ void st_cg(uint32_t* p, uint32_t v) { __stcg(p, v); }
+
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
+
+}  // namespace ws

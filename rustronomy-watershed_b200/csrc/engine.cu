@@ -1,0 +1,912 @@
+// engine.cu -- host side of the engine: context, workspaces, the kernel
+// pipeline, and the extern "C" boundary declared in include/ws_b200.h.
+//
+// Pipeline of one run (all on the context's stream, no host round trip except
+// where noted):
+//   fill_state -> seed_init -> flood (persistent, cooperative)
+//   -> parent -> jump (persistent, cooperative)                      [labels + levels]
+//   merging only: edge_hist -> edge_scan -> (host reads the edge total, grows the
+//   edge buffer if needed) -> edge_scatter -> uf_init -> union_levels (persistent,
+//   cooperative) -> lake_counts
+#include "../../include/ws_b200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace ws;
+
+// ---------------------------------------------------------------------------
+// context / plan objects
+// ---------------------------------------------------------------------------
+
+struct ws_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  int flood_grid = 0, jump_grid = 0, union_grid = 0;
+  std::string err;
+  ws_plan* cached = nullptr;  // workspace reused by the host-level entry points
+  // host-level scratch (device)
+  uint8_t* d_img = nullptr;   size_t d_img_cap = 0;
+  uint8_t* d_raw = nullptr;   size_t d_raw_cap = 0;
+  uint32_t* d_seeds = nullptr; size_t d_seeds_cap = 0;  // [cap][2]
+  uint32_t* d_seed_off = nullptr; size_t d_seed_off_cap = 0;
+  uint64_t* d_out[2] = {nullptr, nullptr}; size_t d_out_cap[2] = {0, 0};
+  uint64_t* h_pin[2] = {nullptr, nullptr}; size_t h_pin_cap[2] = {0, 0};
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+};
+
+struct ws_plan {
+  ws_ctx* ctx = nullptr;
+  ImageDims d{};
+  FloodBuffers fb{};
+  MergeBuffers mb{};
+  size_t uf_cap = 0, edges_cap = 0, rep_cap = 0;
+  uint32_t* rep = nullptr;
+  int rep_level = -1;
+  uint32_t* chunk_counts = nullptr;  // minima scratch
+  uint32_t* d_total = nullptr;
+  uint32_t* h_ctrl = nullptr;        // pinned mirror of fb.ctrl + scalars
+  // last run
+  const uint32_t* seeds = nullptr;
+  const uint32_t* seed_off = nullptr;
+  std::vector<uint32_t> h_seed_off;
+  size_t nseeds = 0;
+  ws_config cfg{};
+  bool ran = false, merged = false;
+  uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+ws_status fail(ws_ctx* ctx, ws_status s, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return s;
+}
+
+ws_status cuda_fail(ws_ctx* ctx, cudaError_t e, const char* what) {
+  cudaGetLastError();  // clear the sticky-free error state
+  std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+  return fail(ctx, e == cudaErrorMemoryAllocation ? WS_ERR_OOM : WS_ERR_CUDA, m);
+}
+
+#define WS_CUDA(ctx, expr)                                        \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return cuda_fail((ctx), _e, #expr);    \
+  } while (0)
+
+#define WS_TRY(expr)                      \
+  do {                                    \
+    ws_status _s = (expr);                \
+    if (_s != WS_OK) return _s;           \
+  } while (0)
+
+template <typename T>
+ws_status grow(ws_ctx* ctx, T*& p, size_t& cap, size_t need) {
+  if (need <= cap && p) return WS_OK;
+  if (p) WS_CUDA(ctx, cudaFree(p));
+  p = nullptr;
+  cap = 0;
+  const size_t n = std::max<size_t>(need, 1);
+  WS_CUDA(ctx, cudaMalloc((void**)&p, n * sizeof(T)));
+  cap = n;
+  return WS_OK;
+}
+
+ImageDims make_dims(size_t n_img, size_t rows, size_t cols) {
+  ImageDims d;
+  d.n_img = (int)n_img;
+  d.rows = (int)rows;
+  d.cols = (int)cols;
+  d.tiles_x = (int)((cols + TILE_W - 1) / TILE_W);
+  d.tiles_y = (int)((rows + TILE_H - 1) / TILE_H);
+  return d;
+}
+
+ws_status check_cfg(ws_ctx* ctx, const ws_config* cfg) {
+  if (!cfg) return fail(ctx, WS_ERR_INVALID_ARG, "cfg is NULL");
+  ws_status s = ws_config_validate(cfg);
+  if (s != WS_OK) return fail(ctx, s, ws_status_str(s));
+  return WS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------
+
+extern "C" const char* ws_status_str(ws_status s) {
+  switch (s) {
+    case WS_OK: return "ok";
+    case WS_ERR_INVALID_ARG: return "invalid argument";
+    case WS_ERR_MAX_TOO_HIGH: return "maximum water level higher than the maximum allowed value 254";
+    case WS_ERR_MAX_TOO_LOW: return "maximum water level lower than the minimum allowed value 1";
+    case WS_ERR_SEED_OOB: return "seed outside the (padded) image";
+    case WS_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+    case WS_ERR_CUDA: return "CUDA error";
+    case WS_ERR_OOM: return "out of device memory";
+    case WS_ERR_TOO_LARGE: return "image or seed list too large";
+    case WS_ERR_HOP_OVERFLOW: return "flood path longer than 2^24-2 steps inside one level";
+    case WS_ERR_INTERNAL: return "internal error";
+  }
+  return "unknown status";
+}
+
+extern "C" int ws_abi_version(void) { return WS_ABI_VERSION; }
+extern "C" void ws_free(void* p) { free(p); }
+extern "C" const char* ws_last_error(const ws_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+extern "C" ws_status ws_config_validate(const ws_config* cfg) {
+  if (!cfg) return WS_ERR_INVALID_ARG;
+  if (cfg->kind != WS_SEGMENTING && cfg->kind != WS_MERGING) return WS_ERR_INVALID_ARG;
+  if (cfg->max_water_level > WS_NORMAL_MAX) return WS_ERR_MAX_TOO_HIGH;   // lib.rs:1000 / 1026
+  if (cfg->max_water_level <= WS_ALWAYS_FILL) return WS_ERR_MAX_TOO_LOW;  // lib.rs:1002 / 1028
+  if (cfg->reserved != 0) return WS_ERR_INVALID_ARG;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_output_shape(const ws_config* cfg, size_t rows, size_t cols, size_t* out_rows,
+                                     size_t* out_cols) {
+  if (!cfg || !out_rows || !out_cols) return WS_ERR_INVALID_ARG;
+  const size_t pad = cfg->edge_correction ? 2 : 0;  // lib.rs:1330-1336
+  *out_rows = rows + pad;
+  *out_cols = cols + pad;
+  return WS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+
+extern "C" ws_status ws_ctx_create(int device, ws_ctx** out) {
+  if (!out) return WS_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return WS_ERR_NO_DEVICE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return WS_ERR_NO_DEVICE;
+  int coop = 0, major = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (!coop || major < 10) return WS_ERR_NO_DEVICE;  // sm_100a code only
+  ws_ctx* c = new (std::nothrow) ws_ctx();
+  if (!c) return WS_ERR_INTERNAL;
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return WS_ERR_CUDA;
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+  }
+  c->flood_grid = flood_max_grid(device);
+  c->jump_grid = jump_max_grid(device);
+  c->union_grid = union_max_grid(device);
+  if (c->flood_grid <= 0 || c->jump_grid <= 0 || c->union_grid <= 0) {
+    cudaGetLastError();
+    ws_ctx_destroy(c);
+    return WS_ERR_CUDA;  // e.g. the fatbin holds no code for this GPU
+  }
+  *out = c;
+  return WS_OK;
+}
+
+extern "C" void ws_ctx_destroy(ws_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+  if (c->cached) ws_plan_destroy(c->cached);
+  cudaFree(c->d_img);
+  cudaFree(c->d_raw);
+  cudaFree(c->d_seeds);
+  cudaFree(c->d_seed_off);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(c->d_out[i]);
+    if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
+    if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]);
+    if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+  }
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+extern "C" void* ws_ctx_stream(ws_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" ws_status ws_ctx_synchronize(ws_ctx* ctx) {
+  if (!ctx) return WS_ERR_INVALID_ARG;
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return WS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+
+extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size_t cols, ws_plan** out) {
+  if (!ctx || !out) return WS_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (n_img == 0 || rows == 0 || cols == 0) return fail(ctx, WS_ERR_INVALID_ARG, "empty image");
+  // pixel indices live in 31 bits of a label word
+  if (rows > 0x7fffffffull || cols > 0x7fffffffull || n_img > 0x7fffffffull ||
+      (double)n_img * (double)rows * (double)cols >= 2147483648.0)
+    return fail(ctx, WS_ERR_TOO_LARGE, "more than 2^31 - 1 pixels in one plan");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  ws_plan* p = new (std::nothrow) ws_plan();
+  if (!p) return WS_ERR_INTERNAL;
+  p->ctx = ctx;
+  p->d = make_dims(n_img, rows, cols);
+  const size_t npx = p->d.px_total();
+  const size_t ntiles = (size_t)p->d.tiles_total();
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** ptr, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(ptr, std::max<size_t>(bytes, 16));
+  };
+  alloc((void**)&p->fb.T, npx * 4);
+  alloc((void**)&p->fb.lab, npx * 4);
+  alloc((void**)&p->fb.lvl, npx);
+  alloc((void**)&p->fb.lists, ntiles * 3 * 4);
+  alloc((void**)&p->fb.flags, ntiles * 4);
+  alloc((void**)&p->fb.ctrl, FC_WORDS * 4);
+  alloc((void**)&p->mb.level_hist, 257 * 4);
+  alloc((void**)&p->mb.level_cursor, 256 * 4);
+  alloc((void**)&p->mb.unions, n_img * 256 * 4);
+  alloc((void**)&p->mb.ndistinct, n_img * 4);
+  alloc((void**)&p->mb.counts, n_img * 256 * 4);
+  alloc((void**)&p->chunk_counts, minima_num_chunks(p->d) * 4);
+  alloc((void**)&p->d_total, 16);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_ctrl, (FC_WORDS + 4) * 4);
+  if (e != cudaSuccess) {
+    ws_plan_destroy(p);
+    return cuda_fail(ctx, e, "ws_plan_create");
+  }
+  *out = p;
+  return WS_OK;
+}
+
+extern "C" void ws_plan_destroy(ws_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->ctx->device);
+  cudaStreamSynchronize(p->ctx->stream);
+  if (p->ctx->cached == p) p->ctx->cached = nullptr;
+  cudaFree(p->fb.T);
+  cudaFree(p->fb.lab);
+  cudaFree(p->fb.lvl);
+  cudaFree(p->fb.lists);
+  cudaFree(p->fb.flags);
+  cudaFree(p->fb.ctrl);
+  cudaFree(p->mb.level_hist);
+  cudaFree(p->mb.level_cursor);
+  cudaFree(p->mb.edges);
+  cudaFree(p->mb.parent);
+  cudaFree(p->mb.hook_to);
+  cudaFree(p->mb.hook_lvl);
+  cudaFree(p->mb.unions);
+  cudaFree(p->mb.ndistinct);
+  cudaFree(p->mb.counts);
+  cudaFree(p->rep);
+  cudaFree(p->chunk_counts);
+  cudaFree(p->d_total);
+  if (p->h_ctrl) cudaFreeHost(p->h_ctrl);
+  delete p;
+}
+
+extern "C" ws_status ws_plan_find_local_minima(ws_plan* p, const uint8_t* d_imgs, uint32_t* d_seeds_rc, size_t cap,
+                                               uint32_t* d_seed_off, size_t* out_total) {
+  if (!p || !d_imgs || !d_seed_off || !out_total) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t nchunks = minima_num_chunks(p->d);
+  WS_CUDA(ctx, launch_minima_count(d_imgs, p->d, p->chunk_counts, s));
+  WS_CUDA(ctx, launch_minima_scan(p->chunk_counts, nchunks, p->d, d_seed_off, p->d_total, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS, p->d_total, 4, cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));
+  const size_t total = p->h_ctrl[FC_WORDS];
+  *out_total = total;
+  p->stats[4] += 2;
+  if (total > cap || !d_seeds_rc) {
+    if (total == 0) return WS_OK;
+    return fail(ctx, WS_ERR_TOO_LARGE, "seed buffer too small for the minima found");
+  }
+  if (total) {
+    WS_CUDA(ctx, launch_minima_write(d_imgs, p->d, p->chunk_counts, d_seeds_rc, (uint32_t)cap, s));
+    p->stats[4] += 1;
+  }
+  return WS_OK;
+}
+
+static ws_status plan_merge(ws_plan* p) {
+  ws_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  const uint32_t lmax = p->cfg.max_water_level;
+  // union-find arrays sized to the seed list
+  if (p->nseeds > p->uf_cap || !p->mb.parent) {
+    cudaFree(p->mb.parent); cudaFree(p->mb.hook_to); cudaFree(p->mb.hook_lvl);
+    p->mb.parent = p->mb.hook_to = nullptr; p->mb.hook_lvl = nullptr; p->uf_cap = 0;
+    const size_t n = std::max<size_t>(p->nseeds, 1);
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.parent, n * 4));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_to, n * 4));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_lvl, n));
+    p->uf_cap = n;
+  }
+  WS_CUDA(ctx, launch_edge_hist(p->fb.lab, p->fb.lvl, p->d, p->mb.level_hist, s));
+  WS_CUDA(ctx, launch_edge_scan(p->mb.level_hist, p->mb.level_cursor, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.level_hist + 256, 4, cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));  // the only mid-pipeline host round trip: size of the edge list
+  const size_t nedges = p->h_ctrl[FC_WORDS + 1];
+  if (nedges > p->edges_cap || !p->mb.edges) {
+    cudaFree(p->mb.edges);
+    p->mb.edges = nullptr; p->edges_cap = 0;
+    const size_t n = std::max<size_t>(nedges + nedges / 8, 1024);
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.edges, n * sizeof(uint2)));
+    p->edges_cap = n;
+  }
+  if (nedges) WS_CUDA(ctx, launch_edge_scatter(p->fb.lab, p->fb.lvl, p->d, p->seed_off, p->mb.level_cursor, p->mb.edges, s));
+  WS_CUDA(ctx, launch_uf_init(p->mb, p->fb.lab, p->d, p->seeds, p->seed_off, (uint32_t)p->nseeds, s));
+  if (nedges) WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
+  WS_CUDA(ctx, launch_lake_counts(p->mb, p->d.n_img, lmax, s));
+  p->stats[3] = nedges;
+  p->stats[4] += 4 + (nedges ? 2 : 0);
+  p->merged = true;
+  p->rep_level = -1;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t* d_imgs, const uint32_t* d_seeds_rc,
+                                 const uint32_t* d_seed_off, size_t nseeds_total) {
+  if (!p || !d_imgs || !d_seed_off || (nseeds_total && !d_seeds_rc)) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  WS_TRY(check_cfg(ctx, cfg));
+  if (nseeds_total >= 0x7fffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "more than 2^31 - 2 seeds");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  p->cfg = *cfg;
+  p->seeds = d_seeds_rc;
+  p->seed_off = d_seed_off;
+  p->nseeds = nseeds_total;
+  p->ran = false;
+  p->merged = false;
+  for (auto& v : p->stats) v = 0;
+
+  // hop counters can only overflow when a single slice has more than 2^24 pixels
+  const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
+  WS_CUDA(ctx, launch_fill_state(p->fb, p->d, s));
+  WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, s));
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, d_imgs, cfg->max_water_level, check_ovf, ctx->flood_grid, s));
+  WS_CUDA(ctx, launch_parent(p->fb, p->d, s));
+  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
+  p->stats[4] += 4 + (nseeds_total ? 1 : 0);
+  if (cfg->kind == WS_MERGING) WS_TRY(plan_merge(p));
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl, p->fb.ctrl, FC_WORDS * 4, cudaMemcpyDeviceToHost, s));
+  p->h_seed_off.resize((size_t)p->d.n_img + 1);  // colour base of every slice, for merging snapshots
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_seed_off.data(), d_seed_off, ((size_t)p->d.n_img + 1) * 4,
+                               cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));
+  p->stats[0] = p->h_ctrl[FC_SWEEPS];
+  p->stats[1] = p->h_ctrl[FC_ACTIVATIONS];
+  p->stats[2] = p->h_ctrl[FC_JUMP_ROUNDS];
+  const uint32_t err = p->h_ctrl[FC_ERROR];
+  if (err & 1u) return fail(ctx, WS_ERR_SEED_OOB, "a seed lies outside the image");
+  if (err & 2u) return fail(ctx, WS_ERR_HOP_OVERFLOW, ws_status_str(WS_ERR_HOP_OVERFLOW));
+  if (err & 4u) return fail(ctx, WS_ERR_INTERNAL, "flood did not reach a fixed point");
+  p->ran = true;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_dev_malloc(ws_ctx* ctx, size_t bytes, void** out) {
+  if (!ctx || !out) return WS_ERR_INVALID_ARG;
+  *out = nullptr;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, cudaMalloc(out, std::max<size_t>(bytes, 16)));
+  return WS_OK;
+}
+extern "C" ws_status ws_dev_free(ws_ctx* ctx, void* d_ptr) {
+  if (!ctx) return WS_ERR_INVALID_ARG;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  WS_CUDA(ctx, cudaFree(d_ptr));
+  return WS_OK;
+}
+extern "C" ws_status ws_memcpy_h2d(ws_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (!ctx || (bytes && (!d_dst || !h_src))) return WS_ERR_INVALID_ARG;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return WS_OK;
+}
+extern "C" ws_status ws_memcpy_d2h(ws_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (!ctx || (bytes && (!h_dst || !d_src))) return WS_ERR_INVALID_ARG;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return WS_OK;
+}
+
+extern "C" const uint32_t* ws_plan_arrival_times(const ws_plan* p) { return p ? p->fb.T : nullptr; }
+extern "C" const uint32_t* ws_plan_labels(const ws_plan* p) { return p ? p->fb.lab : nullptr; }
+extern "C" const uint8_t* ws_plan_levels(const ws_plan* p) { return p ? p->fb.lvl : nullptr; }
+extern "C" const uint32_t* ws_plan_lake_counts(const ws_plan* p) { return p ? p->mb.counts : nullptr; }
+
+static ws_status plan_rep_table(ws_plan* p, uint32_t level) {
+  ws_ctx* ctx = p->ctx;
+  if (!p->merged) return fail(ctx, WS_ERR_INVALID_ARG, "merging snapshot requested but the last run was not WS_MERGING");
+  if (p->nseeds > p->rep_cap || !p->rep) {
+    cudaFree(p->rep);
+    p->rep = nullptr; p->rep_cap = 0; p->rep_level = -1;
+    const size_t n = std::max<size_t>(p->nseeds, 1);
+    WS_CUDA(ctx, cudaMalloc((void**)&p->rep, n * 4));
+    p->rep_cap = n;
+  }
+  if (p->rep_level == (int)level) return WS_OK;
+  const int incremental = (p->rep_level >= 0 && p->rep_level < (int)level) ? 1 : 0;
+  WS_CUDA(ctx, launch_rep_table(p->mb.hook_to, p->mb.hook_lvl, (uint32_t)p->nseeds, level, incremental, p->rep,
+                                ctx->stream));
+  p->rep_level = (int)level;
+  p->stats[4] += 1;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_snapshot(ws_plan* p, ws_kind kind, size_t i, uint8_t level, uint64_t* d_out) {
+  if (!p || !d_out) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  if (!p->ran) return fail(ctx, WS_ERR_INVALID_ARG, "no completed run to snapshot");
+  if (i >= (size_t)p->d.n_img) return fail(ctx, WS_ERR_INVALID_ARG, "slice index out of range");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = p->d.px_per_img();
+  const uint32_t* rep = nullptr;
+  uint32_t base = 0;
+  if (kind == WS_MERGING) {
+    WS_TRY(plan_rep_table(p, level));
+    rep = p->rep;
+    base = p->h_seed_off.size() > i ? p->h_seed_off[i] : 0;
+  }
+  WS_CUDA(ctx, launch_snapshot(p->fb.lab + i * n, p->fb.lvl + i * n, n, level, rep, base, d_out, ctx->stream));
+  p->stats[4] += 1;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_stats(ws_plan* p, uint64_t out[8]) {
+  if (!p || !out) return WS_ERR_INVALID_ARG;
+  for (int i = 0; i < 8; ++i) out[i] = p->stats[i];
+  return WS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-level entry points (the reference-facing ones)
+// ---------------------------------------------------------------------------
+
+namespace {
+
+ws_status check_image(ws_ctx* ctx, const ws_image* img) {
+  if (!img || !img->data) return fail(ctx, WS_ERR_INVALID_ARG, "image is NULL");
+  if (img->rows == 0 || img->cols == 0) return fail(ctx, WS_ERR_INVALID_ARG, "empty image");
+  return WS_OK;
+}
+
+// Upload an ArrayView2<u8> (arbitrary strides) as a dense C-order device image.
+ws_status upload_image(ws_ctx* ctx, const ws_image* img, uint8_t* dst) {
+  cudaStream_t s = ctx->stream;
+  const size_t rows = img->rows, cols = img->cols;
+  if (img->col_stride == 1 && img->row_stride == (ptrdiff_t)cols) {
+    WS_CUDA(ctx, cudaMemcpyAsync(dst, img->data, rows * cols, cudaMemcpyHostToDevice, s));
+  } else if (img->col_stride == 1 && img->row_stride > (ptrdiff_t)cols) {
+    WS_CUDA(ctx, cudaMemcpy2DAsync(dst, cols, img->data, (size_t)img->row_stride, cols, rows,
+                                   cudaMemcpyHostToDevice, s));
+  } else {  // general strides (transposed / reversed views): repack on the host
+    std::vector<uint8_t> tmp(rows * cols);
+    for (size_t r = 0; r < rows; ++r)
+      for (size_t c = 0; c < cols; ++c)
+        tmp[r * cols + c] = img->data[(ptrdiff_t)r * img->row_stride + (ptrdiff_t)c * img->col_stride];
+    WS_CUDA(ctx, cudaMemcpyAsync(dst, tmp.data(), rows * cols, cudaMemcpyHostToDevice, s));
+    WS_CUDA(ctx, cudaStreamSynchronize(s));  // tmp dies here
+  }
+  return WS_OK;
+}
+
+ws_status get_plan(ws_ctx* ctx, size_t n_img, size_t rows, size_t cols, ws_plan** out) {
+  ws_plan* p = ctx->cached;
+  if (p && p->d.n_img == (int)n_img && p->d.rows == (int)rows && p->d.cols == (int)cols) {
+    *out = p;
+    return WS_OK;
+  }
+  if (p) ws_plan_destroy(p);
+  ctx->cached = nullptr;
+  WS_TRY(ws_plan_create(ctx, n_img, rows, cols, &p));
+  ctx->cached = p;
+  *out = p;
+  return WS_OK;
+}
+
+// Everything the host-level calls share: validate, upload image (+pad) and seeds, run.
+struct HostRun {
+  ws_plan* plan = nullptr;
+  size_t orows = 0, ocols = 0, npx = 0;
+};
+
+ws_status host_run_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs, const ws_image* view, size_t n_img,
+                         size_t rows, size_t cols, const uint64_t* seeds_rc, const uint64_t* seed_offsets,
+                         size_t nseeds, HostRun* hr) {
+  WS_TRY(check_cfg(ctx, cfg));
+  if (nseeds && !seeds_rc) return fail(ctx, WS_ERR_INVALID_ARG, "seeds is NULL");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t orows, ocols;
+  ws_output_shape(cfg, rows, cols, &orows, &ocols);
+  // the reference indexes output[seed] on the (padded) output shape and panics when outside
+  for (size_t i = 0; i < nseeds; ++i)
+    if (seeds_rc[2 * i] >= orows || seeds_rc[2 * i + 1] >= ocols)
+      return fail(ctx, WS_ERR_SEED_OOB, "seed " + std::to_string(i) + " lies outside the image");
+  ws_plan* p = nullptr;
+  WS_TRY(get_plan(ctx, n_img, orows, ocols, &p));
+  cudaStream_t s = ctx->stream;
+  const size_t npx_in = rows * cols, npx_out = orows * ocols;
+  WS_TRY(grow(ctx, ctx->d_img, ctx->d_img_cap, n_img * npx_out));
+  if (cfg->edge_correction) {
+    WS_TRY(grow(ctx, ctx->d_raw, ctx->d_raw_cap, n_img * npx_in));
+    if (view) WS_TRY(upload_image(ctx, view, ctx->d_raw));
+    else WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_raw, imgs, n_img * npx_in, cudaMemcpyHostToDevice, s));
+    for (size_t b = 0; b < n_img; ++b)
+      WS_CUDA(ctx, launch_pad_image(ctx->d_raw + b * npx_in, (int)rows, (int)cols, ctx->d_img + b * npx_out, s));
+  } else {
+    if (view) WS_TRY(upload_image(ctx, view, ctx->d_img));
+    else WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_img, imgs, n_img * npx_in, cudaMemcpyHostToDevice, s));
+  }
+  // seeds: (usize, usize) pairs -> u32 pairs; offsets
+  std::vector<uint32_t> h_seeds(2 * std::max<size_t>(nseeds, 1));
+  for (size_t i = 0; i < 2 * nseeds; ++i) h_seeds[i] = (uint32_t)seeds_rc[i];
+  p->h_seed_off.assign(n_img + 1, 0);
+  if (seed_offsets) {
+    for (size_t b = 0; b <= n_img; ++b) p->h_seed_off[b] = (uint32_t)seed_offsets[b];
+  } else {
+    p->h_seed_off[n_img] = (uint32_t)nseeds;
+  }
+  WS_TRY(grow(ctx, ctx->d_seeds, ctx->d_seeds_cap, 2 * nseeds));
+  WS_TRY(grow(ctx, ctx->d_seed_off, ctx->d_seed_off_cap, n_img + 1));
+  if (nseeds) WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds, h_seeds.data(), 2 * nseeds * 4, cudaMemcpyHostToDevice, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seed_off, p->h_seed_off.data(), (n_img + 1) * 4, cudaMemcpyHostToDevice, s));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));  // h_seeds dies at return
+  WS_TRY(ws_plan_run(p, cfg, ctx->d_img, ctx->d_seeds, ctx->d_seed_off, nseeds));
+  hr->plan = p;
+  hr->orows = orows;
+  hr->ocols = ocols;
+  hr->npx = npx_out;
+  return WS_OK;
+}
+
+ws_status host_run(ws_ctx* ctx, const ws_config* cfg, const ws_image* img, const uint64_t* seeds_rc, size_t nseeds,
+                   HostRun* hr) {
+  if (!ctx) return WS_ERR_INVALID_ARG;
+  WS_TRY(check_image(ctx, img));
+  return host_run_batch(ctx, cfg, nullptr, img, 1, img->rows, img->cols, seeds_rc, nullptr, nseeds, hr);
+}
+
+// Per-level snapshots streamed to the host: kernel into one of two device buffers on the
+// compute stream, device->host copy on the copy stream, double buffered.  `sink` receives
+// (level, host pointer valid until the next but one call) -- or the copy goes straight to
+// `direct` + level * npx when that is given.
+template <typename Sink>
+ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint64_t* direct, Sink sink) {
+  ws_plan* p = hr.plan;
+  const size_t npx = hr.npx;
+  const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
+  for (int i = 0; i < 2; ++i) {
+    WS_TRY(grow(ctx, ctx->d_out[i], ctx->d_out_cap[i], npx));
+    if (!direct && ctx->h_pin_cap[i] < npx) {
+      if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
+      ctx->h_pin[i] = nullptr; ctx->h_pin_cap[i] = 0;
+      WS_CUDA(ctx, cudaMallocHost((void**)&ctx->h_pin[i], npx * 8));
+      ctx->h_pin_cap[i] = npx;
+    }
+  }
+  const ws_kind kind = (ws_kind)cfg->kind;
+  for (uint32_t l = 0; l <= nlev; ++l) {
+    const int buf = l & 1;
+    if (l < nlev) {
+      if (l >= 2) WS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+      WS_TRY(ws_plan_snapshot(p, kind, 0, (uint8_t)l, ctx->d_out[buf]));
+      WS_CUDA(ctx, cudaEventRecord(ctx->ev_ready[buf], ctx->stream));
+      WS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[buf], 0));
+      uint64_t* dst = direct ? direct + (size_t)l * npx : ctx->h_pin[buf];
+      WS_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_out[buf], npx * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      WS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+    }
+    if (l >= 1 && !direct) {  // hand level l-1 to the sink while level l is in flight
+      const int pb = (l - 1) & 1;
+      WS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[pb]));
+      sink((uint8_t)(l - 1), ctx->h_pin[pb]);
+    }
+  }
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return WS_OK;
+}
+
+}  // namespace
+
+extern "C" ws_status ws_find_local_minima_batch(ws_ctx* ctx, const uint8_t* imgs, size_t n_img, size_t rows,
+                                                size_t cols, uint64_t** out_rc, uint64_t* out_offsets) {
+  if (!ctx || !imgs || !out_rc || !out_offsets) return WS_ERR_INVALID_ARG;
+  *out_rc = nullptr;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n_img == 0 || rows == 0 || cols == 0) return fail(ctx, WS_ERR_INVALID_ARG, "empty image");
+  ws_plan* p = nullptr;
+  WS_TRY(get_plan(ctx, n_img, rows, cols, &p));
+  cudaStream_t s = ctx->stream;
+  const size_t npx = n_img * rows * cols;
+  WS_TRY(grow(ctx, ctx->d_img, ctx->d_img_cap, npx));
+  WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_img, imgs, npx, cudaMemcpyHostToDevice, s));
+  WS_TRY(grow(ctx, ctx->d_seed_off, ctx->d_seed_off_cap, n_img + 1));
+  size_t total = 0;
+  ws_status st = ws_plan_find_local_minima(p, ctx->d_img, nullptr, 0, ctx->d_seed_off, &total);
+  if (st != WS_OK && st != WS_ERR_TOO_LARGE) return st;
+  ctx->err.clear();
+  WS_TRY(grow(ctx, ctx->d_seeds, ctx->d_seeds_cap, 2 * total));
+  if (total) WS_CUDA(ctx, launch_minima_write(ctx->d_img, p->d, p->chunk_counts, ctx->d_seeds, (uint32_t)total, s));
+  std::vector<uint32_t> h(2 * std::max<size_t>(total, 1)), hoff(n_img + 1);
+  if (total) WS_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->d_seeds, 2 * total * 4, cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(hoff.data(), ctx->d_seed_off, (n_img + 1) * 4, cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));
+  uint64_t* out = (uint64_t*)malloc(std::max<size_t>(2 * total, 1) * sizeof(uint64_t));
+  if (!out) return fail(ctx, WS_ERR_INTERNAL, "host allocation failed");
+  for (size_t i = 0; i < 2 * total; ++i) out[i] = h[i];
+  for (size_t b = 0; b <= n_img; ++b) out_offsets[b] = hoff[b];
+  *out_rc = out;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_find_local_minima(ws_ctx* ctx, const ws_image* img, uint64_t** out_rc, size_t* out_n) {
+  if (!ctx || !out_rc || !out_n) return WS_ERR_INVALID_ARG;
+  *out_rc = nullptr;
+  *out_n = 0;
+  WS_TRY(check_image(ctx, img));
+  const bool dense = img->col_stride == 1 && img->row_stride == (ptrdiff_t)img->cols;
+  std::vector<uint8_t> tmp;
+  const uint8_t* src = img->data;
+  if (!dense) {
+    tmp.resize(img->rows * img->cols);
+    for (size_t r = 0; r < img->rows; ++r)
+      for (size_t c = 0; c < img->cols; ++c)
+        tmp[r * img->cols + c] = img->data[(ptrdiff_t)r * img->row_stride + (ptrdiff_t)c * img->col_stride];
+    src = tmp.data();
+  }
+  uint64_t off[2] = {0, 0};
+  WS_TRY(ws_find_local_minima_batch(ctx, src, 1, img->rows, img->cols, out_rc, off));
+  *out_n = (size_t)off[1];
+  return WS_OK;
+}
+
+extern "C" ws_status ws_transform(ws_ctx* ctx, const ws_config* cfg, const ws_image* img, const uint64_t* seeds_rc,
+                                  size_t nseeds, uint64_t* out_labels) {
+  if (!ctx || !out_labels) return WS_ERR_INVALID_ARG;
+  WS_TRY(check_cfg(ctx, cfg));
+  WS_TRY(check_image(ctx, img));
+  if (cfg->kind == WS_MERGING) {
+    // lib.rs:1524-1536: image and seeds are ignored, the shape is the INPUT shape (no padding)
+    const size_t rows = img->rows, cols = img->cols;
+    memset(out_labels, 0, rows * cols * sizeof(uint64_t));
+    if (rows >= 3 && cols >= 3)
+      for (size_t r = 1; r + 1 < rows; ++r)
+        for (size_t c = 1; c + 1 < cols; ++c) out_labels[r * cols + c] = 123;
+    return WS_OK;
+  }
+  HostRun hr;
+  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
+  WS_TRY(grow(ctx, ctx->d_out[0], ctx->d_out_cap[0], hr.npx));
+  WS_CUDA(ctx, launch_widen_labels(hr.plan->fb.lab, hr.npx, ctx->d_out[0], ctx->stream));
+  WS_CUDA(ctx, cudaMemcpyAsync(out_labels, ctx->d_out[0], hr.npx * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  hr.plan->stats[4] += 1;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_transform_compact(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
+                                          const uint64_t* seeds_rc, size_t nseeds, uint32_t* out_labels,
+                                          uint8_t* out_level) {
+  if (!ctx) return WS_ERR_INVALID_ARG;
+  HostRun hr;
+  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
+  if (out_labels) {
+    WS_TRY(grow(ctx, ctx->d_out[0], ctx->d_out_cap[0], (hr.npx + 1) / 2));
+    WS_CUDA(ctx, launch_strip_labels(hr.plan->fb.lab, hr.npx, (uint32_t*)ctx->d_out[0], ctx->stream));
+    WS_CUDA(ctx, cudaMemcpyAsync(out_labels, ctx->d_out[0], hr.npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    hr.plan->stats[4] += 1;
+  }
+  if (out_level)
+    WS_CUDA(ctx, cudaMemcpyAsync(out_level, hr.plan->fb.lvl, hr.npx, cudaMemcpyDeviceToHost, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return WS_OK;
+}
+
+extern "C" ws_status ws_transform_history(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
+                                          const uint64_t* seeds_rc, size_t nseeds, uint8_t* out_levels,
+                                          uint64_t* out_labels) {
+  if (!ctx || !out_labels) return WS_ERR_INVALID_ARG;
+  HostRun hr;
+  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
+  if (out_levels)
+    for (uint32_t l = 0; l <= cfg->max_water_level; ++l) out_levels[l] = (uint8_t)l;
+  return stream_snapshots(ctx, hr, cfg, out_labels, [](uint8_t, const uint64_t*) {});
+}
+
+extern "C" ws_status ws_transform_with_hook(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
+                                            const uint64_t* seeds_rc, size_t nseeds, ws_level_hook hook, void* user) {
+  if (!ctx) return WS_ERR_INVALID_ARG;
+  HostRun hr;
+  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
+  if (!hook) return WS_OK;  // no hook: the reference returns an empty Vec (lib.rs:1510, 1520)
+  // host copies of what HookCtx exposes: the (padded) image and the (colour, (row, col)) list
+  std::vector<uint8_t> h_img(hr.npx);
+  WS_CUDA(ctx, cudaMemcpyAsync(h_img.data(), ctx->d_img, hr.npx, cudaMemcpyDeviceToHost, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<uint64_t> h_seeds(3 * std::max<size_t>(nseeds, 1));
+  for (size_t i = 0; i < nseeds; ++i) {
+    h_seeds[3 * i] = i + 1;
+    h_seeds[3 * i + 1] = seeds_rc[2 * i];
+    h_seeds[3 * i + 2] = seeds_rc[2 * i + 1];
+  }
+  ws_hook_ctx hc;
+  hc.max_water_level = cfg->max_water_level;
+  hc.image = h_img.data();
+  hc.rows = hr.orows;
+  hc.cols = hr.ocols;
+  hc.seeds = h_seeds.data();
+  hc.nseeds = nseeds;
+  return stream_snapshots(ctx, hr, cfg, nullptr, [&](uint8_t level, const uint64_t* colours) {
+    hc.water_level = level;
+    hc.colours = colours;
+    hook(user, &hc);
+  });
+}
+
+extern "C" ws_status ws_transform_lake_counts(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
+                                              const uint64_t* seeds_rc, size_t nseeds, uint64_t* out_lake_counts,
+                                              uint64_t* out_uncoloured) {
+  if (!ctx) return WS_ERR_INVALID_ARG;
+  HostRun hr;
+  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
+  ws_plan* p = hr.plan;
+  cudaStream_t s = ctx->stream;
+  const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
+  std::vector<uint32_t> h_hist(256), h_counts(256);
+  // level histogram -> uncoloured pixels per level (d_total scratch is too small: reuse unions' sibling)
+  uint32_t* d_hist = nullptr;
+  WS_CUDA(ctx, cudaMalloc((void**)&d_hist, 256 * 4));
+  cudaError_t e = launch_level_hist(p->fb.lvl, p->d, d_hist, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_hist.data(), d_hist, 256 * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && cfg->kind == WS_MERGING)
+    e = cudaMemcpyAsync(h_counts.data(), p->mb.counts, 256 * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_hist);
+  if (e != cudaSuccess) return cuda_fail(ctx, e, "ws_transform_lake_counts");
+  p->stats[4] += 1;
+  if (cfg->kind == WS_SEGMENTING) {
+    // no merges: every colour present on the canvas is a lake at every level
+    std::vector<uint32_t> nd(1);
+    MergeBuffers& m = p->mb;
+    // count distinct colours with the same kernel the merging path uses
+    if (p->nseeds > p->uf_cap || !m.parent) {
+      cudaFree(m.parent); cudaFree(m.hook_to); cudaFree(m.hook_lvl);
+      m.parent = m.hook_to = nullptr; m.hook_lvl = nullptr; p->uf_cap = 0;
+      const size_t n = std::max<size_t>(p->nseeds, 1);
+      WS_CUDA(ctx, cudaMalloc((void**)&m.parent, n * 4));
+      WS_CUDA(ctx, cudaMalloc((void**)&m.hook_to, n * 4));
+      WS_CUDA(ctx, cudaMalloc((void**)&m.hook_lvl, n));
+      p->uf_cap = n;
+    }
+    WS_CUDA(ctx, launch_uf_init(m, p->fb.lab, p->d, p->seeds, p->seed_off, (uint32_t)p->nseeds, s));
+    WS_CUDA(ctx, cudaMemcpyAsync(nd.data(), m.ndistinct, 4, cudaMemcpyDeviceToHost, s));
+    WS_CUDA(ctx, cudaStreamSynchronize(s));
+    for (uint32_t l = 0; l < nlev; ++l) h_counts[l] = nd[0];
+    p->stats[4] += 1;
+  }
+  uint64_t coloured = 0;
+  for (uint32_t l = 0; l < nlev; ++l) {
+    coloured += h_hist[l];
+    if (out_lake_counts) out_lake_counts[l] = h_counts[l];
+    if (out_uncoloured) out_uncoloured[l] = (uint64_t)hr.npx - coloured;
+  }
+  return WS_OK;
+}
+
+extern "C" ws_status ws_transform_to_list(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
+                                          const uint64_t* seeds_rc, size_t nseeds, uint8_t* out_levels,
+                                          uint64_t* out_sizes) {
+  if (!ctx || !out_sizes) return WS_ERR_INVALID_ARG;
+  HostRun hr;
+  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
+  ws_plan* p = hr.plan;
+  cudaStream_t s = ctx->stream;
+  const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
+  const size_t ncol = nseeds + 1;  // labels never exceed nseeds: the rest of each row is zero
+  if ((double)ncol * nlev * 12.0 > 64e9) return fail(ctx, WS_ERR_TOO_LARGE, "transform_to_list: nseeds x levels too large");
+  uint32_t* d_cnt = nullptr;
+  uint64_t* d_sizes = nullptr;
+  uint64_t* d_scratch = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_cnt, ncol * nlev * 4);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_sizes, ncol * nlev * 8);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_scratch, ncol * 8);
+  ws_status st = WS_OK;
+  auto body = [&]() -> ws_status {
+    WS_CUDA(ctx, e);
+    WS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, ncol * nlev * 4, s));
+    WS_CUDA(ctx, cudaMemsetAsync(d_sizes, 0, ncol * nlev * 8, s));
+    WS_CUDA(ctx, launch_colour_level_count(p->fb.lab, p->fb.lvl, hr.npx, (uint32_t)ncol, d_cnt, s));
+    WS_CUDA(ctx, launch_sizes_cumulate(d_cnt, (uint32_t)ncol, nlev, hr.npx, d_sizes, s));
+    p->stats[4] += 3;
+    if (cfg->kind == WS_MERGING) {
+      for (uint32_t l = 0; l < nlev; ++l) {
+        WS_TRY(plan_rep_table(p, l));
+        WS_CUDA(ctx, launch_sizes_fold(d_sizes + (size_t)l * ncol, p->rep, (uint32_t)ncol, d_scratch, s));
+        p->stats[4] += 1;
+      }
+    }
+    // rows of length npx+1 on the host (find_lake_sizes, lib.rs:630): zero, then the first ncol entries
+    const size_t row = hr.npx + 1;
+    memset(out_sizes, 0, (size_t)nlev * row * sizeof(uint64_t));
+    WS_CUDA(ctx, cudaMemcpy2DAsync(out_sizes, row * 8, d_sizes, ncol * 8, ncol * 8, nlev, cudaMemcpyDeviceToHost, s));
+    WS_CUDA(ctx, cudaStreamSynchronize(s));
+    return WS_OK;
+  };
+  st = body();
+  cudaFree(d_cnt);
+  cudaFree(d_sizes);
+  cudaFree(d_scratch);
+  if (st == WS_OK && out_levels)
+    for (uint32_t l = 0; l < nlev; ++l) out_levels[l] = (uint8_t)l;
+  return st;
+}
+
+extern "C" ws_status ws_transform_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs, size_t n_img,
+                                        size_t rows, size_t cols, const uint64_t* seeds_rc,
+                                        const uint64_t* seed_offsets, uint64_t* out_labels,
+                                        uint64_t* out_lake_counts) {
+  if (!ctx || !imgs || !seed_offsets) return WS_ERR_INVALID_ARG;
+  if (n_img == 0 || rows == 0 || cols == 0) return fail(ctx, WS_ERR_INVALID_ARG, "empty image");
+  for (size_t b = 0; b < n_img; ++b)
+    if (seed_offsets[b] > seed_offsets[b + 1]) return fail(ctx, WS_ERR_INVALID_ARG, "seed_offsets must be ascending");
+  const size_t nseeds = (size_t)seed_offsets[n_img];
+  HostRun hr;
+  WS_TRY(host_run_batch(ctx, cfg, imgs, nullptr, n_img, rows, cols, seeds_rc, seed_offsets, nseeds, &hr));
+  ws_plan* p = hr.plan;
+  cudaStream_t s = ctx->stream;
+  const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
+  if (out_labels) {
+    for (size_t b = 0; b < n_img; ++b) {
+      const int buf = (int)(b & 1);
+      WS_TRY(grow(ctx, ctx->d_out[buf], ctx->d_out_cap[buf], hr.npx));
+      if (b >= 2) WS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_copied[buf], 0));
+      WS_CUDA(ctx, launch_widen_labels(p->fb.lab + b * hr.npx, hr.npx, ctx->d_out[buf], s));
+      WS_CUDA(ctx, cudaEventRecord(ctx->ev_ready[buf], s));
+      WS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[buf], 0));
+      WS_CUDA(ctx, cudaMemcpyAsync(out_labels + b * hr.npx, ctx->d_out[buf], hr.npx * 8, cudaMemcpyDeviceToHost,
+                                   ctx->copy_stream));
+      WS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+      p->stats[4] += 1;
+    }
+    WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  }
+  if (out_lake_counts) {
+    if (cfg->kind != WS_MERGING) return fail(ctx, WS_ERR_INVALID_ARG, "lake counts need kind = WS_MERGING");
+    std::vector<uint32_t> h(n_img * 256);
+    WS_CUDA(ctx, cudaMemcpyAsync(h.data(), p->mb.counts, n_img * 256 * 4, cudaMemcpyDeviceToHost, s));
+    WS_CUDA(ctx, cudaStreamSynchronize(s));
+    for (size_t b = 0; b < n_img; ++b)
+      for (uint32_t l = 0; l < nlev; ++l) out_lake_counts[b * nlev + l] = h[b * 256 + l];
+  }
+  WS_CUDA(ctx, cudaStreamSynchronize(s));
+  return WS_OK;
+}

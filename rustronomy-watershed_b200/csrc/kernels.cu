@@ -1,0 +1,926 @@
+// kernels.cu -- hand-written sm_100a kernels of the watershed hot path.
+//
+// Every kernel is integer, HBM/L2/shared-memory bound work; there is no dense
+// contraction anywhere on this path, so no tensor-core code.  What matters
+// here: coalesced row-major access, shared-memory staging of tiles with their
+// halo, persistent cooperative grids sized to the co-resident CTA count
+// (multiples of the 148 SMs), and as few passes over HBM as possible.
+#include "kernels.cuh"
+
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace ws {
+
+// ===========================================================================
+// K1  find_local_minima  (lib.rs:1178-1197)
+//
+// One CTA = one row segment of MINIMA_CHUNK columns, 4 pixels per thread.
+// Chunks are numbered row-major (slice, row, segment), so an exclusive scan of
+// the per-chunk counts followed by an in-chunk rank reproduces the row-major
+// order of the reference's `collect()`.
+// ===========================================================================
+
+__device__ __forceinline__ uint32_t minima_mask4(const uint8_t* __restrict__ img, const ImageDims& d, int b, int r,
+                                                 int c0) {
+  // bit k set <=> pixel (r, c0+k) is an interior pixel strictly greater than its 8 neighbours
+  if (r < 1 || r > d.rows - 2) return 0u;
+  const uint8_t* base = img + (size_t)b * d.px_per_img();
+  const uint8_t* up = base + (size_t)(r - 1) * d.cols;
+  const uint8_t* mid = up + d.cols;
+  const uint8_t* dn = mid + d.cols;
+  uint32_t u[6], m[6], l[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const int c = c0 - 1 + k;
+    const bool in = (c >= 0 && c < d.cols);
+    u[k] = in ? __ldg(up + c) : 0u;
+    m[k] = in ? __ldg(mid + c) : 0u;
+    l[k] = in ? __ldg(dn + c) : 0u;
+  }
+  uint32_t mask = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + k;
+    if (c < 1 || c > d.cols - 2) continue;
+    const uint32_t t = m[k + 1];
+    // max of the 8 neighbours must be < t   (lib.rs:1190: all(|val| val < target_val))
+    uint32_t nb = max(max(u[k], u[k + 1]), u[k + 2]);
+    nb = max(nb, max(m[k], m[k + 2]));
+    nb = max(nb, max(max(l[k], l[k + 1]), l[k + 2]));
+    if (nb < t) mask |= 1u << k;
+  }
+  return mask;
+}
+
+__device__ __forceinline__ void minima_chunk_coords(const ImageDims& d, size_t chunk, int& b, int& r, int& c0) {
+  const int segs = (d.cols + MINIMA_CHUNK - 1) / MINIMA_CHUNK;
+  const size_t per_img = (size_t)d.rows * segs;
+  b = (int)(chunk / per_img);
+  const size_t rem = chunk - (size_t)b * per_img;
+  r = (int)(rem / segs);
+  c0 = (int)(rem - (size_t)r * segs) * MINIMA_CHUNK + threadIdx.x * 4;
+}
+
+__global__ void __launch_bounds__(256) minima_count_kernel(const uint8_t* __restrict__ img, ImageDims d,
+                                                           uint32_t* __restrict__ chunk_counts) {
+  __shared__ uint32_t s_warp[8];
+  int b, r, c0;
+  minima_chunk_coords(d, blockIdx.x, b, r, c0);
+  uint32_t n = __popc(minima_mask4(img, d, b, r, c0));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_warp[w];
+    chunk_counts[blockIdx.x] = t;
+  }
+}
+
+// Single-CTA exclusive scan (n_chunks is at most a few 100k; ~tens of microseconds).
+__global__ void __launch_bounds__(1024) minima_scan_kernel(uint32_t* __restrict__ v, size_t n, ImageDims d,
+                                                           uint32_t* __restrict__ seed_off,
+                                                           uint32_t* __restrict__ total) {
+  __shared__ uint32_t s_part[1024];
+  const size_t per = (n + 1023) / 1024;
+  const size_t lo = min(n, (size_t)threadIdx.x * per), hi = min(n, lo + per);
+  uint32_t sum = 0;
+  for (size_t i = lo; i < hi; ++i) sum += v[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the 1024 partials
+  for (int o = 1; o < 1024; o <<= 1) {
+    uint32_t add = (threadIdx.x >= (unsigned)o) ? s_part[threadIdx.x - o] : 0u;
+    __syncthreads();
+    s_part[threadIdx.x] += add;
+    __syncthreads();
+  }
+  uint32_t run = (threadIdx.x == 0) ? 0u : s_part[threadIdx.x - 1];
+  for (size_t i = lo; i < hi; ++i) {
+    const uint32_t c = v[i];
+    v[i] = run;
+    run += c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) total[0] = s_part[1023];
+  // offsets of the slices = offset of each slice's first chunk
+  const int segs = (d.cols + MINIMA_CHUNK - 1) / MINIMA_CHUNK;
+  const size_t per_img = (size_t)d.rows * segs;
+  for (int b = threadIdx.x; b <= d.n_img; b += 1024)
+    seed_off[b] = (b == d.n_img) ? s_part[1023] : v[(size_t)b * per_img];
+}
+
+__global__ void __launch_bounds__(256) minima_write_kernel(const uint8_t* __restrict__ img, ImageDims d,
+                                                           const uint32_t* __restrict__ chunk_offsets,
+                                                           uint32_t* __restrict__ out_rc, uint32_t cap) {
+  __shared__ uint32_t s_warp[8];
+  int b, r, c0;
+  minima_chunk_coords(d, blockIdx.x, b, r, c0);
+  const uint32_t mask = minima_mask4(img, d, b, r, c0);
+  const uint32_t n = __popc(mask);
+  // exclusive rank inside the CTA, in column order
+  uint32_t incl = n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t pre = 0;
+  for (int w = 0; w < warp; ++w) pre += s_warp[w];
+  uint32_t pos = chunk_offsets[blockIdx.x] + pre + incl - n;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (mask & (1u << k)) {
+      if (pos < cap) {
+        out_rc[2 * (size_t)pos] = (uint32_t)r;
+        out_rc[2 * (size_t)pos + 1] = (uint32_t)(c0 + k);
+      }
+      ++pos;
+    }
+  }
+}
+
+size_t minima_num_chunks(const ImageDims& d) {
+  const size_t segs = (d.cols + MINIMA_CHUNK - 1) / MINIMA_CHUNK;
+  return (size_t)d.n_img * d.rows * segs;
+}
+
+cudaError_t launch_minima_count(const uint8_t* img, ImageDims d, uint32_t* chunk_counts, cudaStream_t s) {
+  minima_count_kernel<<<(unsigned)minima_num_chunks(d), 256, 0, s>>>(img, d, chunk_counts);
+  return cudaGetLastError();
+}
+cudaError_t launch_minima_scan(uint32_t* chunk_counts, size_t n_chunks, ImageDims d, uint32_t* seed_off,
+                               uint32_t* total, cudaStream_t s) {
+  minima_scan_kernel<<<1, 1024, 0, s>>>(chunk_counts, n_chunks, d, seed_off, total);
+  return cudaGetLastError();
+}
+cudaError_t launch_minima_write(const uint8_t* img, ImageDims d, const uint32_t* chunk_offsets, uint32_t* out_rc,
+                                uint32_t cap, cudaStream_t s) {
+  minima_write_kernel<<<(unsigned)minima_num_chunks(d), 256, 0, s>>>(img, d, chunk_offsets, out_rc, cap);
+  return cudaGetLastError();
+}
+
+// ===========================================================================
+// K2  flood: arrival times of all water levels in one persistent kernel
+//     (replaces the level loop x 'colouring_loop x find_flooded_px x write-back,
+//      lib.rs:1379-1438 / 1689-1748 and 196-257)
+// ===========================================================================
+
+__global__ void __launch_bounds__(256) fill_state_kernel(uint32_t* __restrict__ T, uint32_t* __restrict__ lab,
+                                                         size_t n) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    __stcg(T + i, T_INF);
+    __stcg(lab + i, 0u);
+  }
+}
+
+cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, cudaStream_t s) {
+  const size_t n = d.px_total();
+  const unsigned grid = (unsigned)min((size_t)148 * 16, (n + 255) / 256);
+  fill_state_kernel<<<grid ? grid : 1, 256, 0, s>>>(b.T, b.lab, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (size_t)d.tiles_total(), s);
+  if (e != cudaSuccess) return e;
+  return cudaMemsetAsync(b.ctrl, 0, sizeof(uint32_t) * FC_WORDS, s);
+}
+
+__device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t ntiles, int list, uint32_t tile) {
+  const uint32_t bit = 1u << list;
+  const uint32_t old = atomicOr(&b.flags[tile], bit);
+  if (!(old & bit)) {
+    const uint32_t pos = atomicAdd(&b.ctrl[FC_COUNT0 + list], 1u);
+    st_cg(&b.lists[(size_t)list * ntiles + pos], tile);
+  }
+}
+
+// Colour the starting pixels (lib.rs:1365-1367): T = 0, colour = index + 1, a later
+// duplicate overwrites an earlier one (sequential loop) == the largest index wins.
+__global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDims d,
+                                                        const uint32_t* __restrict__ seeds_rc,
+                                                        const uint32_t* __restrict__ seed_off, uint32_t nseeds) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseeds) return;
+  // slice of seed i: last b with seed_off[b] <= i
+  int lo = 0, hi = d.n_img;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
+  }
+  const int img = lo;
+  const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
+  if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) {
+    atomicOr(&b.ctrl[FC_ERROR], 1u);
+    return;
+  }
+  const size_t p = (size_t)img * d.px_per_img() + (size_t)r * d.cols + c;
+  st_cg(&b.T[p], 0u);
+  atomicMax(&b.lab[p], LAB_RESOLVED | (i - __ldg(seed_off + img) + 1u));
+  const uint32_t ntiles = (uint32_t)d.tiles_total();
+  const int ty = r / TILE_H, tx = c / TILE_W;
+  const uint32_t tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
+  push_tile(b, ntiles, 0, tile);
+  if (r % TILE_H == 0 && ty > 0) push_tile(b, ntiles, 0, tile - d.tiles_x);
+  if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile(b, ntiles, 0, tile + d.tiles_x);
+  if (c % TILE_W == 0 && tx > 0) push_tile(b, ntiles, 0, tile - 1);
+  if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile(b, ntiles, 0, tile + 1);
+}
+
+cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
+                             uint32_t nseeds, cudaStream_t s) {
+  if (nseeds == 0) return cudaSuccess;
+  seed_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds);
+  return cudaGetLastError();
+}
+
+struct FloodArgs {
+  FloodBuffers b;
+  ImageDims d;
+  const uint8_t* img;
+  uint32_t lmax;
+  int check_overflow;
+};
+
+enum { EDGE_UP = 1, EDGE_DOWN = 2, EDGE_LEFT = 4, EDGE_RIGHT = 8 };
+
+// Bring one tile (with its 1-pixel halo staged in shared memory) to its local
+// fixed point, write the changed pixels back and queue the neighbours whose
+// halo changed.
+__device__ __forceinline__ void flood_tile(const FloodArgs& a, uint32_t tile, int cur, int nxt, uint32_t* sT,
+                                           uint32_t* s_edge) {
+  const ImageDims& d = a.d;
+  const int tpi = d.tiles_per_img();
+  const int img = tile / tpi;
+  const int trem = tile - img * tpi;
+  const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
+  const int r0 = ty * TILE_H, c0 = tx * TILE_W;
+  const size_t base = (size_t)img * d.px_per_img();
+  uint32_t* Tg = a.b.T + base;
+
+  // stage T + halo; coalesced along rows.  Out-of-image cells never matter:
+  // only border pixels touch them and border pixels have A = T_INF.
+  for (int i = threadIdx.x; i < SM_H * SM_W; i += FLOOD_THREADS) {
+    const int lr = i / SM_W, lc = i - lr * SM_W;
+    const int r = r0 - 1 + lr, c = c0 - 1 + lc;
+    uint32_t v = T_INF;
+    if (r >= 0 && r < d.rows && c >= 0 && c < d.cols) v = ld_cg(Tg + (size_t)r * d.cols + c);
+    sT[i] = v;
+  }
+  if (threadIdx.x == 0) {
+    *s_edge = 0;
+    atomicAnd(&a.b.flags[tile], ~(1u << cur));
+    atomicAdd(&a.b.ctrl[FC_ACTIVATIONS], 1u);
+  }
+
+  const int lc = threadIdx.x % TILE_W;       // column inside the tile
+  const int g = threadIdx.x / TILE_W;        // row group
+  const int c = c0 + lc;
+  const int rb = r0 + g * ROWS_PER_THREAD;
+  uint32_t A[ROWS_PER_THREAD], t[ROWS_PER_THREAD];
+  const uint8_t* ig = a.img + base;
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+    const int r = rb + i;
+    // only window centres flood (lib.rs:220), and only pixels at or below the
+    // last water level (filter (1), lib.rs:224, over levels 0..=max)
+    const bool interior = (r >= 1 && r <= d.rows - 2 && c >= 1 && c <= d.cols - 2);
+    uint32_t v = 255u;
+    if (interior) v = __ldg(ig + (size_t)r * d.cols + c);
+    A[i] = (interior && v <= a.lmax) ? ((v << 24) | 1u) : T_INF;
+  }
+  __syncthreads();
+  uint32_t* col = sT + (g * ROWS_PER_THREAD + 1) * SM_W + lc + 1;  // my first pixel
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) t[i] = col[i * SM_W];
+
+  uint32_t chg = 0;
+  bool ovf = false;
+  int any;
+  do {
+    const uint32_t up = col[-SM_W];
+    const uint32_t dn = col[ROWS_PER_THREAD * SM_W];
+    uint32_t mlr[ROWS_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) mlr[i] = min(col[i * SM_W - 1], col[i * SM_W + 1]);
+    uint32_t it = 0;
+    // downward Gauss-Seidel pass inside the thread's column strip ...
+    uint32_t prev = up;
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+      const uint32_t below = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : dn;
+      const uint32_t n = max(A[i], umin3(mlr[i], prev, below) + 1u);
+      if (n < t[i]) {
+        t[i] = n;
+        it |= 1u << i;
+        ovf |= ((n & HOP_MASK) == 0u);
+      }
+      prev = t[i];
+    }
+    // ... and upward
+    uint32_t nextv = dn;
+#pragma unroll
+    for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
+      const uint32_t above = (i > 0) ? t[i - 1] : up;
+      const uint32_t n = max(A[i], umin3(mlr[i], above, nextv) + 1u);
+      if (n < t[i]) {
+        t[i] = n;
+        it |= 1u << i;
+        ovf |= ((n & HOP_MASK) == 0u);
+      }
+      nextv = t[i];
+    }
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD; ++i)
+      if (it & (1u << i)) col[i * SM_W] = t[i];
+    chg |= it;
+    any = (it != 0u);
+  } while (__syncthreads_or(any));
+
+  if (chg) {
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD; ++i)
+      if (chg & (1u << i)) st_cg(Tg + (size_t)(rb + i) * d.cols + c, t[i]);
+    uint32_t e = 0;
+    if (lc == 0) e |= EDGE_LEFT;
+    if (lc == TILE_W - 1) e |= EDGE_RIGHT;
+    if (g == 0 && (chg & 1u)) e |= EDGE_UP;
+    if (g == TILE_H / ROWS_PER_THREAD - 1 && (chg & (1u << (ROWS_PER_THREAD - 1)))) e |= EDGE_DOWN;
+    if (e) atomicOr(s_edge, e);
+    if (a.check_overflow && ovf) atomicOr(&a.b.ctrl[FC_ERROR], 2u);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const uint32_t e = *s_edge;
+    const uint32_t ntiles = (uint32_t)d.tiles_total();
+    if (threadIdx.x == 0 && (e & EDGE_UP) && ty > 0) push_tile(a.b, ntiles, nxt, tile - d.tiles_x);
+    if (threadIdx.x == 1 && (e & EDGE_DOWN) && ty + 1 < d.tiles_y) push_tile(a.b, ntiles, nxt, tile + d.tiles_x);
+    if (threadIdx.x == 2 && (e & EDGE_LEFT) && tx > 0) push_tile(a.b, ntiles, nxt, tile - 1);
+    if (threadIdx.x == 3 && (e & EDGE_RIGHT) && tx + 1 < d.tiles_x) push_tile(a.b, ntiles, nxt, tile + 1);
+  }
+}
+
+// Persistent cooperative kernel.  Sweep s drains worklist s%3 (tiles handed out
+// through an atomic cursor), fills worklist (s+1)%3 and resets worklist (s+2)%3;
+// one grid barrier per sweep; ends when a sweep starts with an empty list.
+__global__ void __launch_bounds__(FLOOD_THREADS) flood_kernel(FloodArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t sT[SM_H * SM_W];
+  __shared__ uint32_t s_tile, s_edge;
+  const uint32_t ntiles = (uint32_t)a.d.tiles_total();
+  int cur = 0;
+  for (;;) {
+    const uint32_t n = ld_cg(&a.b.ctrl[FC_COUNT0 + cur]);
+    if (n == 0) break;
+    const int nxt = (cur + 1) % 3, old = (cur + 2) % 3;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st_cg(&a.b.ctrl[FC_COUNT0 + old], 0u);
+      st_cg(&a.b.ctrl[FC_CURSOR0 + old], 0u);
+      atomicAdd(&a.b.ctrl[FC_SWEEPS], 1u);
+    }
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_tile = atomicAdd(&a.b.ctrl[FC_CURSOR0 + cur], 1u);
+      __syncthreads();
+      const uint32_t k = s_tile;
+      if (k >= n) break;
+      const uint32_t tile = ld_cg(&a.b.lists[(size_t)cur * ntiles + k]);
+      flood_tile(a, tile, cur, nxt, sT, &s_edge);
+    }
+    grid.sync();
+    cur = nxt;
+  }
+}
+
+static int coop_max_grid(const void* fn, int threads, int device) {
+  int per_sm = 0, sms = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return per_sm * sms;
+}
+
+int flood_max_grid(int device) { return coop_max_grid((const void*)flood_kernel, FLOOD_THREADS, device); }
+
+cudaError_t launch_flood(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, int check_overflow,
+                         int grid, cudaStream_t s) {
+  FloodArgs a{b, d, img, lmax, check_overflow};
+  void* args[] = {&a};
+  const int want = d.tiles_total();
+  const int g = want < grid ? (want > 0 ? want : 1) : grid;
+  return cudaLaunchCooperativeKernel((const void*)flood_kernel, dim3(g), dim3(FLOOD_THREADS), args, 0, s);
+}
+
+// ===========================================================================
+// K3  labels: parent pointer (the `col0` decision of lib.rs:235-255) + pointer jumping
+// ===========================================================================
+
+__global__ void __launch_bounds__(256) parent_kernel(FloodBuffers b, ImageDims d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  const int img = blockIdx.z;
+  if (c >= d.cols) return;
+  const size_t base = (size_t)img * d.px_per_img();
+  const size_t p = base + (size_t)r * d.cols + c;
+  const uint32_t t = b.T[p];
+  b.lvl[p] = (t >= T_INF) ? (uint8_t)255 : (uint8_t)(t >> 24);
+  if (t >= T_INF) {
+    b.lab[p] = LAB_RESOLVED;  // UNCOLOURED
+    return;
+  }
+  if (t == 0u) return;  // seed: coloured by seed_init
+  // A coloured non-seed pixel is interior, so all four neighbours exist.  The coloured
+  // neighbours the reference sees when it colours p are exactly those with T(q) < T(p);
+  // `col0` is the first of them in the order down, right, left, up (lib.rs:190, 245).
+  const size_t q_dn = p + d.cols, q_rt = p + 1, q_lf = p - 1, q_up = p - d.cols;
+  size_t q;
+  if (b.T[q_dn] < t) q = q_dn;
+  else if (b.T[q_rt] < t) q = q_rt;
+  else if (b.T[q_lf] < t) q = q_lf;
+  else if (b.T[q_up] < t) q = q_up;
+  else {
+    atomicOr(&b.ctrl[FC_ERROR], 4u);  // cannot happen at a fixed point
+    b.lab[p] = LAB_RESOLVED;
+    return;
+  }
+  b.lab[p] = (uint32_t)q;
+}
+
+cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s) {
+  dim3 grid((d.cols + 255) / 256, d.rows, d.n_img);
+  parent_kernel<<<grid, 256, 0, s>>>(b, d);
+  return cudaGetLastError();
+}
+
+// Pointer jumping to the seed: lab[p] <- lab[lab[p]] until every word is a resolved label.
+// In-place and racy on purpose: whatever a thread reads is a valid ancestor or the final label.
+__global__ void __launch_bounds__(256) jump_kernel(uint32_t* __restrict__ lab, size_t n, uint32_t* ctrl) {
+  cg::grid_group grid = cg::this_grid();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (uint32_t round = 0;; ++round) {
+    const int cur = round % 3;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      st_cg(&ctrl[FC_JUMP_FLAG0 + (round + 1) % 3], 0u);
+      atomicAdd(&ctrl[FC_JUMP_ROUNDS], 1u);
+    }
+    int pending = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const uint32_t v = ld_cg(lab + i);
+      if (!(v & LAB_RESOLVED)) {
+        const uint32_t w = ld_cg(lab + v);
+        st_cg(lab + i, w);
+        if (!(w & LAB_RESOLVED)) pending = 1;
+      }
+    }
+    if (__syncthreads_or(pending) && threadIdx.x == 0) st_cg(&ctrl[FC_JUMP_FLAG0 + cur], 1u);
+    grid.sync();
+    if (ld_cg(&ctrl[FC_JUMP_FLAG0 + cur]) == 0u) break;
+  }
+}
+
+int jump_max_grid(int device) { return coop_max_grid((const void*)jump_kernel, 256, device); }
+
+cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s) {
+  size_t n = d.px_total();
+  uint32_t* lab = b.lab;
+  uint32_t* ctrl = b.ctrl;
+  void* args[] = {&lab, &n, &ctrl};
+  const size_t want = (n + 255) / 256;
+  const int g = (size_t)grid > want ? (int)(want ? want : 1) : grid;
+  return cudaLaunchCooperativeKernel((const void*)jump_kernel, dim3(g), dim3(256), args, 0, s);
+}
+
+// ===========================================================================
+// K4  merging: basin adjacency edges bucketed by level + union-find per level
+//     (find_merge / make_colour_map / recolour, lib.rs:393-542, 590-592)
+//
+// Two adjacent coloured pixels with different segmenting labels a != b belong to
+// the same lake from level w = max(level(p), level(q)) on, provided at least one
+// of them is a window centre (find_merge only looks from interior pixels,
+// lib.rs:411-414).  Processing the edges in level order with a union-find is the
+// reference's per-level closure; the number of successful unions at level w is
+// the number of lakes that disappear at w.
+// ===========================================================================
+
+struct EdgePair {
+  uint32_t a, b, w;
+  bool ok;
+};
+
+__device__ __forceinline__ bool is_interior(const ImageDims& d, int r, int c) {
+  return r >= 1 && r <= d.rows - 2 && c >= 1 && c <= d.cols - 2;
+}
+
+// edges of pixel (r,c) towards its right (k=0) and lower (k=1) neighbour
+__device__ __forceinline__ void pixel_edges(const uint32_t* __restrict__ lab, const uint8_t* __restrict__ lvl,
+                                            const ImageDims& d, int img, int r, int c, EdgePair e[2]) {
+  e[0].ok = e[1].ok = false;
+  const size_t p = (size_t)img * d.px_per_img() + (size_t)r * d.cols + c;
+  const uint32_t a = lab[p] & LAB_MASK;
+  if (a == 0u) return;
+  const uint32_t la = lvl[p];
+  const bool pin = is_interior(d, r, c);
+  if (c + 1 < d.cols) {
+    const uint32_t bq = lab[p + 1] & LAB_MASK;
+    if (bq != 0u && bq != a && (pin || is_interior(d, r, c + 1))) {
+      e[0].ok = true; e[0].a = a; e[0].b = bq; e[0].w = max(la, (uint32_t)lvl[p + 1]);
+    }
+  }
+  if (r + 1 < d.rows) {
+    const uint32_t bq = lab[p + d.cols] & LAB_MASK;
+    if (bq != 0u && bq != a && (pin || is_interior(d, r + 1, c))) {
+      e[1].ok = true; e[1].a = a; e[1].b = bq; e[1].w = max(la, (uint32_t)lvl[p + d.cols]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) edge_hist_kernel(const uint32_t* __restrict__ lab,
+                                                        const uint8_t* __restrict__ lvl, ImageDims d,
+                                                        uint32_t* __restrict__ level_hist) {
+  __shared__ uint32_t s_hist[256];
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < d.cols) {
+    EdgePair e[2];
+    pixel_edges(lab, lvl, d, blockIdx.z, blockIdx.y, c, e);
+    if (e[0].ok) atomicAdd(&s_hist[e[0].w], 1u);
+    if (e[1].ok) atomicAdd(&s_hist[e[1].w], 1u);
+  }
+  __syncthreads();
+  if (s_hist[threadIdx.x]) atomicAdd(&level_hist[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) edge_scan_kernel(uint32_t* level_hist, uint32_t* level_cursor) {
+  __shared__ uint32_t s[256];
+  s[threadIdx.x] = level_hist[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < 256; ++i) {
+      const uint32_t v = s[i];
+      s[i] = run;
+      run += v;
+    }
+    level_hist[256] = run;
+  }
+  __syncthreads();
+  level_hist[threadIdx.x] = s[threadIdx.x];
+  level_cursor[threadIdx.x] = s[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) edge_scatter_kernel(const uint32_t* __restrict__ lab,
+                                                           const uint8_t* __restrict__ lvl, ImageDims d,
+                                                           const uint32_t* __restrict__ seed_off,
+                                                           uint32_t* __restrict__ level_cursor,
+                                                           uint2* __restrict__ edges) {
+  __shared__ uint32_t s_cnt[256], s_base[256];
+  s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  EdgePair e[2];
+  e[0].ok = e[1].ok = false;
+  uint32_t slot[2] = {0, 0};
+  if (c < d.cols) {
+    pixel_edges(lab, lvl, d, blockIdx.z, blockIdx.y, c, e);
+    if (e[0].ok) slot[0] = atomicAdd(&s_cnt[e[0].w], 1u);
+    if (e[1].ok) slot[1] = atomicAdd(&s_cnt[e[1].w], 1u);
+  }
+  __syncthreads();
+  if (s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&level_cursor[threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  const uint32_t gbase = __ldg(seed_off + blockIdx.z) - 1u;  // global colour id = seed_off[img] + colour - 1
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (e[k].ok) edges[s_base[e[k].w] + slot[k]] = make_uint2(gbase + e[k].a, gbase + e[k].b);
+}
+
+cudaError_t launch_edge_hist(const uint32_t* lab, const uint8_t* lvl, ImageDims d, uint32_t* level_hist,
+                             cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(level_hist, 0, 257 * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  dim3 grid((d.cols + 255) / 256, d.rows, d.n_img);
+  edge_hist_kernel<<<grid, 256, 0, s>>>(lab, lvl, d, level_hist);
+  return cudaGetLastError();
+}
+cudaError_t launch_edge_scan(uint32_t* level_hist, uint32_t* level_cursor, cudaStream_t s) {
+  edge_scan_kernel<<<1, 256, 0, s>>>(level_hist, level_cursor);
+  return cudaGetLastError();
+}
+cudaError_t launch_edge_scatter(const uint32_t* lab, const uint8_t* lvl, ImageDims d, const uint32_t* seed_off,
+                                uint32_t* level_cursor, uint2* edges, cudaStream_t s) {
+  dim3 grid((d.cols + 255) / 256, d.rows, d.n_img);
+  edge_scatter_kernel<<<grid, 256, 0, s>>>(lab, lvl, d, seed_off, level_cursor, edges);
+  return cudaGetLastError();
+}
+
+// union-find initialisation + number of colours actually present on the canvas
+// (a seed position overwritten by a later duplicate seed loses its colour, lib.rs:1365-1367)
+__global__ void __launch_bounds__(256) uf_init_kernel(MergeBuffers m, const uint32_t* __restrict__ lab,
+                                                      ImageDims d, const uint32_t* __restrict__ seeds_rc,
+                                                      const uint32_t* __restrict__ seed_off, uint32_t nseeds) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseeds) return;
+  m.parent[i] = i;
+  m.hook_to[i] = i;
+  m.hook_lvl[i] = 255;
+  int lo = 0, hi = d.n_img;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
+  }
+  const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
+  if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) return;
+  const size_t p = (size_t)lo * d.px_per_img() + (size_t)r * d.cols + c;
+  if ((lab[p] & LAB_MASK) == i - __ldg(seed_off + lo) + 1u) atomicAdd(&m.ndistinct[lo], 1u);
+}
+
+cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,
+                           const uint32_t* seed_off, uint32_t nseeds, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(m.unions, 0, sizeof(uint32_t) * 256 * (size_t)d.n_img, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(m.ndistinct, 0, sizeof(uint32_t) * (size_t)d.n_img, s);
+  if (e != cudaSuccess || nseeds == 0) return e;
+  uf_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(m, lab, d, seeds_rc, seed_off, nseeds);
+  return cudaGetLastError();
+}
+
+__device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
+  uint32_t p = ld_cg(parent + x);
+  while (p != x) {
+    const uint32_t gp = ld_cg(parent + p);
+    if (gp != p) st_cg(parent + x, gp);  // path halving; only ever points at an ancestor
+    x = p;
+    p = gp;
+  }
+  return x;
+}
+
+// All levels in one persistent cooperative kernel; a grid barrier separates the levels.
+__global__ void __launch_bounds__(256) union_levels_kernel(MergeBuffers m, const uint32_t* __restrict__ seed_off,
+                                                           int n_img, uint32_t lmax) {
+  cg::grid_group grid = cg::this_grid();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (uint32_t l = 0; l <= lmax; ++l) {
+    const uint32_t lo = __ldg(m.level_hist + l), hi = __ldg(m.level_hist + l + 1);
+    if (lo == hi) continue;  // uniform across the grid
+    for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+      const uint2 e = m.edges[i];
+      uint32_t a = e.x, b = e.y;
+      for (;;) {
+        a = uf_find(m.parent, a);
+        b = uf_find(m.parent, b);
+        if (a == b) break;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }   // hook the larger root under the smaller
+        if (atomicCAS(m.parent + a, a, b) == a) {
+          m.hook_to[a] = b;
+          m.hook_lvl[a] = (uint8_t)l;
+          int s0 = 0, s1 = n_img;
+          while (s1 - s0 > 1) {
+            const int mid = (s0 + s1) >> 1;
+            if (__ldg(seed_off + mid) <= a) s0 = mid; else s1 = mid;
+          }
+          atomicAdd(&m.unions[(size_t)s0 * 256 + l], 1u);
+          break;
+        }
+      }
+    }
+    grid.sync();
+  }
+}
+
+int union_max_grid(int device) { return coop_max_grid((const void*)union_levels_kernel, 256, device); }
+
+cudaError_t launch_union_levels(MergeBuffers m, const uint32_t* seed_off, int n_img, uint32_t lmax, int grid,
+                                cudaStream_t s) {
+  void* args[] = {&m, &seed_off, &n_img, &lmax};
+  return cudaLaunchCooperativeKernel((const void*)union_levels_kernel, dim3(grid), dim3(256), args, 0, s);
+}
+
+// counts[img][l] = colours present - unions at levels <= l
+__global__ void lake_counts_kernel(MergeBuffers m, int n_img, uint32_t lmax) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= n_img) return;
+  uint32_t n = m.ndistinct[img];
+  for (uint32_t l = 0; l < 256; ++l) {
+    if (l <= lmax) n -= m.unions[(size_t)img * 256 + l];
+    m.counts[(size_t)img * 256 + l] = (l <= lmax) ? n : 0u;
+  }
+}
+
+cudaError_t launch_lake_counts(MergeBuffers m, int n_img, uint32_t lmax, cudaStream_t s) {
+  lake_counts_kernel<<<(n_img + 63) / 64, 64, 0, s>>>(m, n_img, lmax);
+  return cudaGetLastError();
+}
+
+// Representative of every colour at `level`: follow the hook links whose level is <= level.
+// Link levels never decrease along a chain (levels are processed in order), so the first
+// link above `level` ends the walk.
+__global__ void __launch_bounds__(256) rep_table_kernel(const uint32_t* __restrict__ hook_to,
+                                                        const uint8_t* __restrict__ hook_lvl, uint32_t nseeds,
+                                                        uint32_t level, int incremental, uint32_t* rep) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseeds) return;
+  uint32_t x = incremental ? rep[i] : i;
+  while (hook_lvl[x] <= level) x = hook_to[x];
+  rep[i] = x;
+}
+
+cudaError_t launch_rep_table(const uint32_t* hook_to, const uint8_t* hook_lvl, uint32_t nseeds, uint32_t level,
+                             int incremental, uint32_t* rep, cudaStream_t s) {
+  if (nseeds == 0) return cudaSuccess;
+  rep_table_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(hook_to, hook_lvl, nseeds, level, incremental, rep);
+  return cudaGetLastError();
+}
+
+// ===========================================================================
+// K5-K7  per-level outputs
+// ===========================================================================
+
+__global__ void __launch_bounds__(256) snapshot_kernel(const uint32_t* __restrict__ lab,
+                                                       const uint8_t* __restrict__ lvl, size_t n, uint32_t level,
+                                                       const uint32_t* __restrict__ rep, uint32_t colour_base,
+                                                       uint64_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t v = 0;
+    if (lvl[i] <= level) {
+      v = lab[i] & LAB_MASK;
+      if (rep && v) v = rep[colour_base + v - 1u] - colour_base + 1u;
+    }
+    out[i] = v;
+  }
+}
+
+static unsigned stream_grid(size_t n) {
+  const size_t want = (n + 255) / 256;
+  const size_t cap = (size_t)148 * 16;
+  return (unsigned)(want < cap ? (want ? want : 1) : cap);
+}
+
+cudaError_t launch_snapshot(const uint32_t* lab, const uint8_t* lvl, size_t n_px, uint32_t level,
+                            const uint32_t* rep, uint32_t colour_base, uint64_t* out, cudaStream_t s) {
+  snapshot_kernel<<<stream_grid(n_px), 256, 0, s>>>(lab, lvl, n_px, level, rep, colour_base, out);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) widen_kernel(const uint32_t* __restrict__ lab, size_t n,
+                                                    uint64_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = lab[i] & LAB_MASK;
+}
+cudaError_t launch_widen_labels(const uint32_t* lab, size_t n_px, uint64_t* out, cudaStream_t s) {
+  widen_kernel<<<stream_grid(n_px), 256, 0, s>>>(lab, n_px, out);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) strip_kernel(const uint32_t* __restrict__ lab, size_t n,
+                                                    uint32_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = lab[i] & LAB_MASK;
+}
+cudaError_t launch_strip_labels(const uint32_t* lab, size_t n_px, uint32_t* out, cudaStream_t s) {
+  strip_kernel<<<stream_grid(n_px), 256, 0, s>>>(lab, n_px, out);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) level_hist_kernel(const uint8_t* __restrict__ lvl, ImageDims d,
+                                                         uint32_t* __restrict__ lvl_hist) {
+  __shared__ uint32_t s_hist[256];
+  s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t n = d.px_per_img();
+  const uint8_t* base = lvl + (size_t)blockIdx.y * n;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    atomicAdd(&s_hist[base[i]], 1u);
+  __syncthreads();
+  if (s_hist[threadIdx.x]) atomicAdd(&lvl_hist[(size_t)blockIdx.y * 256 + threadIdx.x], s_hist[threadIdx.x]);
+}
+cudaError_t launch_level_hist(const uint8_t* lvl, ImageDims d, uint32_t* lvl_hist, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(lvl_hist, 0, sizeof(uint32_t) * 256 * (size_t)d.n_img, s);
+  if (e != cudaSuccess) return e;
+  const size_t n = d.px_per_img();
+  const unsigned gx = (unsigned)min((size_t)592, (n + 255) / 256);
+  level_hist_kernel<<<dim3(gx ? gx : 1, d.n_img), 256, 0, s>>>(lvl, d, lvl_hist);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) colour_level_count_kernel(const uint32_t* __restrict__ lab,
+                                                                 const uint8_t* __restrict__ lvl, size_t n,
+                                                                 uint32_t ncol, uint32_t* __restrict__ cnt) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t l = lvl[i];
+    if (l == 255u) continue;
+    atomicAdd(&cnt[(size_t)l * ncol + (lab[i] & LAB_MASK)], 1u);
+  }
+}
+cudaError_t launch_colour_level_count(const uint32_t* lab, const uint8_t* lvl, size_t n_px, uint32_t ncol,
+                                      uint32_t* cnt, cudaStream_t s) {
+  colour_level_count_kernel<<<stream_grid(n_px), 256, 0, s>>>(lab, lvl, n_px, ncol, cnt);
+  return cudaGetLastError();
+}
+
+// one thread per colour walks the levels; column 0 (uncoloured) is filled by colour-0's thread
+// from the per-level totals accumulated with one atomic per (colour, level) pair.
+__global__ void __launch_bounds__(256) sizes_cumulate_kernel(const uint32_t* __restrict__ cnt, uint32_t ncol,
+                                                             uint32_t nlevels, uint64_t* __restrict__ sizes) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol || c == 0u) return;
+  uint64_t run = 0;
+  for (uint32_t l = 0; l < nlevels; ++l) {
+    run += cnt[(size_t)l * ncol + c];
+    sizes[(size_t)l * ncol + c] = run;
+  }
+}
+__global__ void __launch_bounds__(256) sizes_uncoloured_kernel(const uint32_t* __restrict__ cnt, uint32_t ncol,
+                                                               uint32_t nlevels, size_t n_px,
+                                                               uint64_t* __restrict__ sizes) {
+  // block l sums row l of cnt; thread 0 of block 0 then turns the totals into the running column 0
+  __shared__ unsigned long long s_sum;
+  __shared__ unsigned long long s_tot[256];
+  for (uint32_t l = 0; l < nlevels; ++l) {
+    if (threadIdx.x == 0) s_sum = 0ull;
+    __syncthreads();
+    unsigned long long acc = 0;
+    for (uint32_t c = 1 + threadIdx.x; c < ncol; c += blockDim.x) acc += cnt[(size_t)l * ncol + c];
+    atomicAdd(&s_sum, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) s_tot[l] = s_sum;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (uint32_t l = 0; l < nlevels; ++l) {
+      run += s_tot[l];
+      sizes[(size_t)l * ncol] = (uint64_t)n_px - run;
+    }
+  }
+}
+cudaError_t launch_sizes_cumulate(const uint32_t* cnt, uint32_t ncol, uint32_t nlevels, size_t n_px,
+                                  uint64_t* sizes, cudaStream_t s) {
+  sizes_cumulate_kernel<<<(ncol + 255) / 256, 256, 0, s>>>(cnt, ncol, nlevels, sizes);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sizes_uncoloured_kernel<<<1, 256, 0, s>>>(cnt, ncol, nlevels, n_px, sizes);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) sizes_fold_kernel(const uint64_t* __restrict__ row,
+                                                         const uint32_t* __restrict__ rep, uint32_t ncol,
+                                                         uint64_t* __restrict__ scratch) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncol || c == 0u) return;
+  const uint64_t v = row[c];
+  if (v) atomicAdd((unsigned long long*)&scratch[rep[c - 1u] + 1u], (unsigned long long)v);
+}
+cudaError_t launch_sizes_fold(uint64_t* sizes_row, const uint32_t* rep, uint32_t ncol, uint64_t* scratch_row,
+                              cudaStream_t s) {
+  // scratch <- 0 ; scratch[rep(c)] += row[c] ; row[1..] <- scratch[1..]   (column 0 is kept)
+  cudaError_t e = cudaMemsetAsync(scratch_row, 0, sizeof(uint64_t) * ncol, s);
+  if (e != cudaSuccess) return e;
+  sizes_fold_kernel<<<(ncol + 255) / 256, 256, 0, s>>>(sizes_row, rep, ncol, scratch_row);
+  e = cudaGetLastError();
+  if (e != cudaSuccess || ncol <= 1) return e;
+  return cudaMemcpyAsync(sizes_row + 1, scratch_row + 1, sizeof(uint64_t) * (ncol - 1), cudaMemcpyDeviceToDevice, s);
+}
+
+__global__ void __launch_bounds__(256) fill_const123_kernel(uint64_t* __restrict__ out, int rows, int cols) {
+  const size_t n = (size_t)rows * cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+    out[i] = (r >= 1 && r <= rows - 2 && c >= 1 && c <= cols - 2) ? 123ull : 0ull;
+  }
+}
+cudaError_t launch_fill_const123(uint64_t* out, int rows, int cols, cudaStream_t s) {
+  fill_const123_kernel<<<stream_grid((size_t)rows * cols), 256, 0, s>>>(out, rows, cols);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) pad_image_kernel(const uint8_t* __restrict__ src, int rows, int cols,
+                                                        uint8_t* __restrict__ dst) {
+  const int pc = cols + 2;
+  const size_t n = (size_t)(rows + 2) * pc;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int r = (int)(i / pc), c = (int)(i - (size_t)r * pc);
+    uint8_t v = 0;
+    if (r >= 1 && r <= rows && c >= 1 && c <= cols) v = src[(size_t)(r - 1) * cols + (c - 1)];
+    dst[i] = v;
+  }
+}
+cudaError_t launch_pad_image(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s) {
+  pad_image_kernel<<<stream_grid((size_t)(rows + 2) * (cols + 2)), 256, 0, s>>>(src, rows, cols, dst);
+  return cudaGetLastError();
+}
+
+}  // namespace ws

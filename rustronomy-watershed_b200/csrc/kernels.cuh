@@ -1,0 +1,105 @@
+// kernels.cuh -- launch wrappers of the sm_100a kernels (kernels.cu).
+// All functions enqueue on `stream` and return the CUDA error of the launch.
+#pragma once
+
+#include "common.cuh"
+
+namespace ws {
+
+// Persistent-kernel control block of the flood (device memory, u32 words).
+enum FloodCtrl {
+  FC_COUNT0 = 0,   // [0..2] entries in worklist 0/1/2
+  FC_CURSOR0 = 3,  // [3..5] next entry to hand out
+  FC_SWEEPS = 6,
+  FC_ACTIVATIONS = 7,
+  FC_ERROR = 8,    // bit 0: seed out of bounds, bit 1: hop overflow, bit 2: orphan pixel
+  FC_JUMP_FLAG0 = 9,  // [9..11] rotating "still unresolved" flags of the pointer jumping
+  FC_JUMP_ROUNDS = 12,
+  FC_WORDS = 16
+};
+
+struct FloodBuffers {
+  uint32_t* T;       // [px_total] arrival times
+  uint32_t* lab;     // [px_total] label / parent words
+  uint8_t* lvl;      // [px_total] level of colouring
+  uint32_t* lists;   // [3][tiles_total] worklists
+  uint32_t* flags;   // [tiles_total] bit k = queued in list k
+  uint32_t* ctrl;    // [FC_WORDS]
+};
+
+// Number of co-resident CTAs a cooperative launch of each persistent kernel may use.
+int flood_max_grid(int device);
+int jump_max_grid(int device);
+int union_max_grid(int device);
+
+// --- seeds (find_local_minima, lib.rs:1178-1197) ---------------------------
+constexpr int MINIMA_CHUNK = 1024;  // columns per chunk (one CTA of 256 threads x 4 px)
+size_t minima_num_chunks(const ImageDims& d);
+cudaError_t launch_minima_count(const uint8_t* img, ImageDims d, uint32_t* chunk_counts, cudaStream_t s);
+// exclusive scan in place; writes seed_off[n_img+1] and total[0]
+cudaError_t launch_minima_scan(uint32_t* chunk_counts, size_t n_chunks, ImageDims d, uint32_t* seed_off,
+                               uint32_t* total, cudaStream_t s);
+cudaError_t launch_minima_write(const uint8_t* img, ImageDims d, const uint32_t* chunk_offsets,
+                                uint32_t* out_rc, uint32_t cap, cudaStream_t s);
+
+// --- flood (find_flooded_px + write-back over all levels, lib.rs:196-257, 1379-1438) ---
+cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, cudaStream_t s);
+cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
+                             uint32_t nseeds, cudaStream_t s);
+cudaError_t launch_flood(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, int check_overflow,
+                         int grid, cudaStream_t s);
+
+// --- labels (colour decision of lib.rs:235-255 with the `col0` tie-break) ---
+cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s);
+cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s);
+
+// --- merging (find_merge + make_colour_map + recolour, lib.rs:393-542, 590-592) ---
+struct MergeBuffers {
+  uint32_t* level_hist;   // [256] edges per level, then exclusive offsets [257]
+  uint32_t* level_cursor; // [256]
+  uint2* edges;           // [n_edges] (global colour id a, b), bucketed by level
+  uint32_t* parent;       // [nseeds] union-find with path halving
+  uint32_t* hook_to;      // [nseeds] immutable link written once when a root is hooked
+  uint8_t* hook_lvl;      // [nseeds] level of that link, 255 = still a root
+  uint32_t* unions;       // [n_img][256] successful unions per level
+  uint32_t* ndistinct;    // [n_img] colours present on the canvas
+  uint32_t* counts;       // [n_img][256] lakes per level
+};
+cudaError_t launch_edge_hist(const uint32_t* lab, const uint8_t* lvl, ImageDims d, uint32_t* level_hist,
+                             cudaStream_t s);
+// level_hist[256] -> exclusive offsets in level_hist[0..256], cursors = offsets
+cudaError_t launch_edge_scan(uint32_t* level_hist, uint32_t* level_cursor, cudaStream_t s);
+cudaError_t launch_edge_scatter(const uint32_t* lab, const uint8_t* lvl, ImageDims d, const uint32_t* seed_off,
+                                uint32_t* level_cursor, uint2* edges, cudaStream_t s);
+cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,
+                           const uint32_t* seed_off, uint32_t nseeds, cudaStream_t s);
+cudaError_t launch_union_levels(MergeBuffers m, const uint32_t* seed_off, int n_img, uint32_t lmax, int grid,
+                                cudaStream_t s);
+cudaError_t launch_lake_counts(MergeBuffers m, int n_img, uint32_t lmax, cudaStream_t s);
+// rep[g] = representative of colour g at `level` (start from rep if `incremental`)
+cudaError_t launch_rep_table(const uint32_t* hook_to, const uint8_t* hook_lvl, uint32_t nseeds, uint32_t level,
+                             int incremental, uint32_t* rep, cudaStream_t s);
+
+// --- per-level outputs (hooks of transform_history / transform_to_list) -----
+// out[p] = lvl[p] <= level ? label : 0, label optionally mapped through rep[] (merging)
+cudaError_t launch_snapshot(const uint32_t* lab, const uint8_t* lvl, size_t n_px, uint32_t level,
+                            const uint32_t* rep, uint32_t colour_base, uint64_t* out, cudaStream_t s);
+cudaError_t launch_widen_labels(const uint32_t* lab, size_t n_px, uint64_t* out, cudaStream_t s);
+cudaError_t launch_strip_labels(const uint32_t* lab, size_t n_px, uint32_t* out, cudaStream_t s);
+// lvl_hist[b][256]: pixels coloured at each level (255 = never)
+cudaError_t launch_level_hist(const uint8_t* lvl, ImageDims d, uint32_t* lvl_hist, cudaStream_t s);
+// cnt[l][c] (row length ncol = nseeds+1): pixels of colour c coloured at level l   (single slice)
+cudaError_t launch_colour_level_count(const uint32_t* lab, const uint8_t* lvl, size_t n_px, uint32_t ncol,
+                                      uint32_t* cnt, cudaStream_t s);
+// sizes[l][c] = sum_{l' <= l} cnt[l'][c] for c >= 1, sizes[l][0] = n_px - sum_c  (find_lake_sizes rows)
+cudaError_t launch_sizes_cumulate(const uint32_t* cnt, uint32_t ncol, uint32_t nlevels, size_t n_px,
+                                  uint64_t* sizes, cudaStream_t s);
+// merging: fold the row of level l through rep[] in place (sizes[l][rep(c)] += sizes[l][c])
+cudaError_t launch_sizes_fold(uint64_t* sizes_row, const uint32_t* rep, uint32_t ncol, uint64_t* scratch_row,
+                              cudaStream_t s);
+// MergingWatershed::transform (lib.rs:1524-1536): interior 123, border 0
+cudaError_t launch_fill_const123(uint64_t* out, int rows, int cols, cudaStream_t s);
+// edge correction (lib.rs:1340-1356): copy into a zeroed canvas one pixel larger on every side
+cudaError_t launch_pad_image(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
+
+}  // namespace ws
