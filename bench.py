@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the watershed hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--size S] [--field uniform|smooth]
+
+Metric: Mpixel*levels/s = (pixels * 255 levels * transforms) / time.  One STEP = the
+segmenting transform and the merging transform (per-level lake counts) of one S x S u8
+field, i.e. 2 * S*S*255 pixel*levels.  Seeds come from find_local_minima and are found
+once, outside the timed region; its time is reported separately.
+
+  value  kernels only: image and seeds already resident in HBM (ws_plan_run through
+         the device-level C ABI), CUDA events on the library's stream;
+  e2e    the reference-facing calls with HOST buffers (Watershed::transform returning
+         usize labels + the merging transform's per-level lake counts), host<->device
+         copies inside the timed region, wall clock around synchronised calls;
+  roofline      the flood kernel against the measured HBM copy peak, algorithmic bytes =
+         9 B per pixel*level;
+  cpu_baseline  the oracle (CPU restatement of the reference, "port") on a bounded crop.
+
+N > 1: one process per GPU (torchrun), every rank runs its own field -- shards, no
+data-path collective ("weak" scaling); barrier + max over ranks for the time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import fieldgen  # noqa: E402
+
+LEVELS = 255                      # water levels 0..=254 (lib.rs:139, 1379)
+ALG_BYTES_PER_PX_LEVEL = 9        # 1 B image + 4 B label read + 4 B label write
+METRIC = "Mpixel*levels/s (full 0..=254 sweep, segmenting + merging)"
+UNIT = "Mpixel*levels/s"
+
+
+def make_field(kind: str, size: int, seed: int) -> np.ndarray:
+    if kind == "uniform":
+        return fieldgen.uniform(size, size, seed)
+    if kind == "smooth":
+        return fieldgen.smooth(size, size, 16.0, seed)
+    raise SystemExit(f"unknown field {kind}")
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py executes oracle/)
+# ---------------------------------------------------------------------------------------
+
+def cpu_sample(field: str, size: int, crop: int, seed: int):
+    """The oracle on a crop of the same workload: both transforms, all host threads, with the
+    reference's own closure (literal make_colour_map).  Returns (Mpx*levels/s, seconds, threads)."""
+    from oracle import oracle as orc
+    orc.build()
+    img = make_field(field, size, seed)[:crop, :crop].copy() if size <= 4096 else make_field(field, crop, seed)
+    seeds = orc.find_local_minima(img)
+    t0 = time.perf_counter()
+    orc.transform(orc.SEGMENTING, img, seeds)                       # Watershed::transform
+    orc.transform(orc.MERGING, img, seeds, fast_closure=False,      # transform_to_list's work
+                  hook=lambda lvl, col: None)
+    dt = time.perf_counter() - t0
+    return 2 * crop * crop * LEVELS / dt / 1e6, dt, orc.num_threads()
+
+
+def reference_arm(args, rank: int):
+    """--impl reference: the reference's CPU path (oracle port; no Rust toolchain here) on the host cores."""
+    if rank != 0:
+        return 0
+    crop = args.cpu_crop
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_sample(args.field, args.size, min(crop, 256), 0)
+    vals, secs = [], []
+    threads = 1
+    t_all = time.perf_counter()
+    for s in range(args.steps):
+        v, dt, threads = cpu_sample(args.field, args.size, crop, s)
+        vals.append(v)
+        secs.append(dt)
+    total = time.perf_counter() - t_all
+    value = args.steps * 2 * crop * crop * LEVELS / sum(secs) / 1e6
+    sample = (f"{crop}x{crop} {args.field} field per step (bounded sample of the {args.size}x{args.size} workload), "
+              "segmenting + merging, literal make_colour_map")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 (integer)",
+        "data": "synthetic",
+        "config": {"workload": f"{args.size}x{args.size} u8 {args.field} field, segmenting + merging, 255 levels",
+                   "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": total,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--field", default="uniform", choices=["uniform", "smooth"])
+    ap.add_argument("--cpu-crop", type=int, default=768, help="side of the CPU baseline's sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    from wsb200_loader import load
+    if args.warmup < 3:
+        print(f"note: --warmup {args.warmup} < 3 breaks the timing rules", file=sys.stderr)
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ws = load()
+    ctx = ws.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    S = args.size
+    npx = S * S
+
+    # ---- workload: one S x S field per rank (inputs >> 126 MB L2 at the default size) ----
+    img_h = torch.from_numpy(make_field(args.field, S, seed=rank)).pin_memory()
+    d_img = img_h.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+    plan = ws.Plan(ctx, 1, S, S)
+    d_off = torch.zeros(2, dtype=torch.int32, device="cuda")
+    t0 = time.perf_counter()
+    nseeds = plan.find_local_minima(d_img.data_ptr(), 0, 0, d_off.data_ptr())        # count
+    d_seeds = torch.empty((max(nseeds, 1), 2), dtype=torch.int32, device="cuda")
+    plan.find_local_minima(d_img.data_ptr(), d_seeds.data_ptr(), nseeds, d_off.data_ptr())
+    ctx.synchronize()
+    seed_ms = 1e3 * (time.perf_counter() - t0)
+
+    def step():
+        plan.run(0, 254, d_img.data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), nseeds)   # segmenting
+        a = plan.phase_ms()
+        la = plan.stats()["kernel_launches"]
+        plan.run(1, 254, d_img.data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), nseeds)   # merging
+        b = plan.phase_ms()
+        return [a["flood"], b["flood"]], la + plan.stats()["kernel_launches"], (a, b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    flood_ms, launches, phases = [], 0, None
+    for _ in range(args.steps):
+        f, l, phases = step()
+        flood_ms += f
+        launches += l
+    ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    stats = plan.stats()
+    if world > 1:
+        t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    px_levels_step = 2 * npx * LEVELS
+    value = world * args.steps * px_levels_step / (dev_ms * 1e-3) / 1e6
+
+    # ---- end to end through the reference-facing API, host buffers (pinned) --------------
+    e2e = None
+    if not args.no_e2e:
+        seg = ws.TransformBuilder.default().set_device(local_rank).build_segmenting()
+        mrg = ws.TransformBuilder.default().set_device(local_rank).build_merging()
+        img_np = img_h.numpy()
+        seeds_h = torch.empty((max(nseeds, 1), 2), dtype=torch.int64).pin_memory()
+        seeds_h.copy_(d_seeds.cpu().to(torch.int64) & 0xFFFFFFFF)
+        seeds_np = seeds_h.numpy().view(np.uint64)[:nseeds]
+        out_h = torch.empty((S, S), dtype=torch.int64).pin_memory()
+        out_np = out_h.numpy().view(np.uint64)
+        plan.close()                                   # the host-level calls bring their own workspace
+        del d_seeds, d_img
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            seg.transform(img_np, seeds_np, out=out_np)          # H2D image+seeds, D2H u64 labels
+            return mrg.lake_counts(img_np, seeds_np)             # H2D image+seeds, D2H per-level counts
+
+        for _ in range(min(args.warmup, 2)):
+            lakes, unc = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            lakes, unc = e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        h2d = 2 * (npx + nseeds * 8)                   # image + u32 seed pairs, both transforms
+        d2h = npx * 8 + 2 * LEVELS * 4 + 1024          # u64 labels + counts + level histogram
+        e2e = {"value": world * args.steps * px_levels_step / e2e_s / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+               "api": "SegmentingWatershed.transform + MergingWatershed.lake_counts (ws_transform, "
+                      "ws_transform_lake_counts), pinned host buffers",
+               "lakes_first_last": [int(lakes[0]), int(lakes[-1])]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (flood) ------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    flood_avg_ms = float(np.mean(flood_ms))
+    alg_bytes = npx * LEVELS * ALG_BYTES_PER_PX_LEVEL
+    achieved = alg_bytes / (flood_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "flood_traffic.json"))).get(f"{args.field}_{S}")
+    except Exception:
+        pass
+    roofline = {"kernel": "flood_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "launch_ms": flood_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "algorithmic bytes = 9 B x pixels x 255 levels (one streaming pass per level, SURVEY 8(d)); "
+                        "the kernel computes all levels in ONE arrival-time propagation, so frac > 1 is expected; "
+                        "traffic = measured DRAM bytes per launch (ncu), see profiles/"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, dt, thr = cpu_sample(args.field, S, args.cpu_crop, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
+               "sample": f"{args.cpu_crop}x{args.cpu_crop} {args.field} crop, segmenting + merging, {dt:.1f} s; "
+                         "CPU restatement of the reference algorithm (no Rust toolchain in the image)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8 image, u32 arrival times / labels (u64 at the API)", "data": "synthetic",
+        "config": {"workload": f"{S}x{S} u8 {args.field} field per GPU, segmenting + merging transform, 255 levels",
+                   "seeds": nseeds, "seed_finding_ms": seed_ms, "l2": "inputs larger than L2 (no flush needed)"
+                   if npx * 9 > 126e6 else "inputs fit in L2",
+                   "parallelism": f"{world} independent fields (shards, no collective)"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        "phases_ms_last_step": {"segmenting": phases[0], "merging": phases[1]},
+        "counters_last_run": stats,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

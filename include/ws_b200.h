@@ -199,7 +199,8 @@ ws_status ws_plan_create(ws_ctx *ctx, size_t n_img, size_t rows, size_t cols,
 void ws_plan_destroy(ws_plan *plan);
 /* Seeds of every slice: d_seeds_rc `[cap][2]` uint32 receives (row, col) in
  * row-major order per slice, d_seed_off[n_img+1] uint32 the offsets.
- * *out_total (host) is the number found; WS_ERR_TOO_LARGE if it exceeds cap.  */
+ * *out_total (host) is the number found; WS_ERR_TOO_LARGE if it exceeds cap.
+ * d_seeds_rc == NULL: count only (offsets and *out_total are still written).  */
 ws_status ws_plan_find_local_minima(ws_plan *plan, const uint8_t *d_imgs,
                                     uint32_t *d_seeds_rc, size_t cap,
                                     uint32_t *d_seed_off, size_t *out_total);
@@ -226,6 +227,11 @@ ws_status ws_plan_snapshot(ws_plan *plan, ws_kind kind, size_t i, uint8_t level,
 /* Counters of the last run: [0] flood sweeps, [1] tile activations,
  * [2] pointer-jumping rounds, [3] merge edges, [4] kernels launched.          */
 ws_status ws_plan_stats(ws_plan *plan, uint64_t out[8]);
+
+/* CUDA-event durations (ms) of the phases of the last run, measured on the ctx stream:
+ * [0] state fill + seed colouring, [1] flood kernel, [2] parent + pointer jumping,
+ * [3] merging (edges, union-find, counts; 0 for segmenting runs).            */
+ws_status ws_plan_phase_ms(ws_plan *plan, float out[4]);
 
 /* ---- plain device-memory helpers for callers without a CUDA runtime of their own ---- */
 ws_status ws_dev_malloc(ws_ctx *ctx, size_t bytes, void **out);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "ws_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "ws_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "ws_plan_stats": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8)]),
+    "ws_plan_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float * 4)]),
 }
 
 _lib = None
@@ -252,6 +253,11 @@ class Plan:
 
     def snapshot(self, kind: int, i: int, level: int, d_out: int):
         self.ctx.check(self.lib.ws_plan_snapshot(self.handle, kind, i, level, d_out))
+
+    def phase_ms(self) -> dict:
+        arr = (C.c_float * 4)()
+        self.ctx.check(self.lib.ws_plan_phase_ms(self.handle, C.byref(arr)))
+        return {"init": arr[0], "flood": arr[1], "labels": arr[2], "merge": arr[3]}
 
     def stats(self) -> dict:
         arr = (C.c_uint64 * 8)()

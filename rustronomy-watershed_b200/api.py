@@ -166,11 +166,15 @@ class Watershed(WatershedUtils, Generic[T]):
         return self.max_water_level + 1                   # 0..=max, lib.rs:1379 / 1689
 
     # -- Watershed::transform --------------------------------------------------
-    def transform(self, input: np.ndarray, seeds: Sequence) -> np.ndarray:
+    def transform(self, input: np.ndarray, seeds: Sequence, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """`out` (extension): a caller-owned C-order uint64 array to fill, e.g. pinned memory."""
         ctx = self._ctx()
         cfg, view, s = self._cfg(), N.image_view(input), N.seeds_array(seeds)
-        shape = input.shape if self.KIND == N.WS_MERGING else self._out_shape(input)
-        out = np.empty(shape, dtype=np.uint64)
+        shape = tuple(input.shape) if self.KIND == N.WS_MERGING else self._out_shape(input)
+        if out is None:
+            out = np.empty(shape, dtype=np.uint64)
+        elif out.shape != shape or out.dtype != np.uint64 or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous uint64 array of shape {shape}")
         ctx.check(ctx.lib.ws_transform(ctx.handle, C.byref(cfg), C.byref(view), s.ctypes.data, s.shape[0],
                                        out.ctypes.data))
         return out

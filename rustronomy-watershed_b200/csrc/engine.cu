@@ -36,6 +36,7 @@ struct ws_ctx {
   uint8_t* d_img = nullptr;   size_t d_img_cap = 0;
   uint8_t* d_raw = nullptr;   size_t d_raw_cap = 0;
   uint32_t* d_seeds = nullptr; size_t d_seeds_cap = 0;  // [cap][2]
+  uint64_t* d_seeds64 = nullptr; size_t d_seeds64_cap = 0;  // staging of the caller's (usize, usize) pairs
   uint32_t* d_seed_off = nullptr; size_t d_seed_off_cap = 0;
   uint64_t* d_out[2] = {nullptr, nullptr}; size_t d_out_cap[2] = {0, 0};
   uint64_t* h_pin[2] = {nullptr, nullptr}; size_t h_pin_cap[2] = {0, 0};
@@ -61,6 +62,7 @@ struct ws_plan {
   ws_config cfg{};
   bool ran = false, merged = false;
   uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last run
 };
 
 namespace {
@@ -212,6 +214,7 @@ extern "C" void ws_ctx_destroy(ws_ctx* c) {
   cudaFree(c->d_img);
   cudaFree(c->d_raw);
   cudaFree(c->d_seeds);
+  cudaFree(c->d_seeds64);
   cudaFree(c->d_seed_off);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->d_out[i]);
@@ -270,6 +273,8 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->chunk_counts, minima_num_chunks(p->d) * 4);
   alloc((void**)&p->d_total, 16);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_ctrl, (FC_WORDS + 4) * 4);
+  for (auto& ev : p->ev)
+    if (e == cudaSuccess) e = cudaEventCreate(&ev);
   if (e != cudaSuccess) {
     ws_plan_destroy(p);
     return cuda_fail(ctx, e, "ws_plan_create");
@@ -302,6 +307,8 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->chunk_counts);
   cudaFree(p->d_total);
   if (p->h_ctrl) cudaFreeHost(p->h_ctrl);
+  for (auto& ev : p->ev)
+    if (ev) cudaEventDestroy(ev);
   delete p;
 }
 
@@ -319,10 +326,8 @@ extern "C" ws_status ws_plan_find_local_minima(ws_plan* p, const uint8_t* d_imgs
   const size_t total = p->h_ctrl[FC_WORDS];
   *out_total = total;
   p->stats[4] += 2;
-  if (total > cap || !d_seeds_rc) {
-    if (total == 0) return WS_OK;
-    return fail(ctx, WS_ERR_TOO_LARGE, "seed buffer too small for the minima found");
-  }
+  if (!d_seeds_rc) return WS_OK;  // count + offsets only
+  if (total > cap) return fail(ctx, WS_ERR_TOO_LARGE, "seed buffer too small for the minima found");
   if (total) {
     WS_CUDA(ctx, launch_minima_write(d_imgs, p->d, p->chunk_counts, d_seeds_rc, (uint32_t)cap, s));
     p->stats[4] += 1;
@@ -385,13 +390,18 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
 
   // hop counters can only overflow when a single slice has more than 2^24 pixels
   const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
+  WS_CUDA(ctx, cudaEventRecord(p->ev[0], s));
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, s));
+  WS_CUDA(ctx, cudaEventRecord(p->ev[1], s));
   WS_CUDA(ctx, launch_flood(p->fb, p->d, d_imgs, cfg->max_water_level, check_ovf, ctx->flood_grid, s));
+  WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
   WS_CUDA(ctx, launch_parent(p->fb, p->d, s));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
+  WS_CUDA(ctx, cudaEventRecord(p->ev[3], s));
   p->stats[4] += 4 + (nseeds_total ? 1 : 0);
   if (cfg->kind == WS_MERGING) WS_TRY(plan_merge(p));
+  WS_CUDA(ctx, cudaEventRecord(p->ev[4], s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl, p->fb.ctrl, FC_WORDS * 4, cudaMemcpyDeviceToHost, s));
   p->h_seed_off.resize((size_t)p->d.n_img + 1);  // colour base of every slice, for merging snapshots
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_seed_off.data(), d_seed_off, ((size_t)p->d.n_img + 1) * 4,
@@ -480,6 +490,13 @@ extern "C" ws_status ws_plan_snapshot(ws_plan* p, ws_kind kind, size_t i, uint8_
   return WS_OK;
 }
 
+extern "C" ws_status ws_plan_phase_ms(ws_plan* p, float out[4]) {
+  if (!p || !out) return WS_ERR_INVALID_ARG;
+  if (!p->ran) return fail(p->ctx, WS_ERR_INVALID_ARG, "no completed run");
+  for (int i = 0; i < 4; ++i) WS_CUDA(p->ctx, cudaEventElapsedTime(&out[i], p->ev[i], p->ev[i + 1]));
+  return WS_OK;
+}
+
 extern "C" ws_status ws_plan_stats(ws_plan* p, uint64_t out[8]) {
   if (!p || !out) return WS_ERR_INVALID_ARG;
   for (int i = 0; i < 8; ++i) out[i] = p->stats[i];
@@ -546,10 +563,6 @@ ws_status host_run_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs,
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   size_t orows, ocols;
   ws_output_shape(cfg, rows, cols, &orows, &ocols);
-  // the reference indexes output[seed] on the (padded) output shape and panics when outside
-  for (size_t i = 0; i < nseeds; ++i)
-    if (seeds_rc[2 * i] >= orows || seeds_rc[2 * i + 1] >= ocols)
-      return fail(ctx, WS_ERR_SEED_OOB, "seed " + std::to_string(i) + " lies outside the image");
   ws_plan* p = nullptr;
   WS_TRY(get_plan(ctx, n_img, orows, ocols, &p));
   cudaStream_t s = ctx->stream;
@@ -565,9 +578,8 @@ ws_status host_run_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs,
     if (view) WS_TRY(upload_image(ctx, view, ctx->d_img));
     else WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_img, imgs, n_img * npx_in, cudaMemcpyHostToDevice, s));
   }
-  // seeds: (usize, usize) pairs -> u32 pairs; offsets
-  std::vector<uint32_t> h_seeds(2 * std::max<size_t>(nseeds, 1));
-  for (size_t i = 0; i < 2 * nseeds; ++i) h_seeds[i] = (uint32_t)seeds_rc[i];
+  // seeds: the (usize, usize) pairs go up as they are; a kernel narrows them to u32 pairs and marks
+  // the ones outside the (padded) output shape -- the reference indexes output[seed] and panics there
   p->h_seed_off.assign(n_img + 1, 0);
   if (seed_offsets) {
     for (size_t b = 0; b <= n_img; ++b) p->h_seed_off[b] = (uint32_t)seed_offsets[b];
@@ -576,9 +588,12 @@ ws_status host_run_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs,
   }
   WS_TRY(grow(ctx, ctx->d_seeds, ctx->d_seeds_cap, 2 * nseeds));
   WS_TRY(grow(ctx, ctx->d_seed_off, ctx->d_seed_off_cap, n_img + 1));
-  if (nseeds) WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds, h_seeds.data(), 2 * nseeds * 4, cudaMemcpyHostToDevice, s));
+  if (nseeds) {
+    WS_TRY(grow(ctx, ctx->d_seeds64, ctx->d_seeds64_cap, 2 * nseeds));
+    WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds64, seeds_rc, 2 * nseeds * 8, cudaMemcpyHostToDevice, s));
+    WS_CUDA(ctx, launch_seeds_convert(ctx->d_seeds64, ctx->d_seeds, nseeds, orows, ocols, s));
+  }
   WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seed_off, p->h_seed_off.data(), (n_img + 1) * 4, cudaMemcpyHostToDevice, s));
-  WS_CUDA(ctx, cudaStreamSynchronize(s));  // h_seeds dies at return
   WS_TRY(ws_plan_run(p, cfg, ctx->d_img, ctx->d_seeds, ctx->d_seed_off, nseeds));
   hr->plan = p;
   hr->orows = orows;
@@ -651,9 +666,7 @@ extern "C" ws_status ws_find_local_minima_batch(ws_ctx* ctx, const uint8_t* imgs
   WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_img, imgs, npx, cudaMemcpyHostToDevice, s));
   WS_TRY(grow(ctx, ctx->d_seed_off, ctx->d_seed_off_cap, n_img + 1));
   size_t total = 0;
-  ws_status st = ws_plan_find_local_minima(p, ctx->d_img, nullptr, 0, ctx->d_seed_off, &total);
-  if (st != WS_OK && st != WS_ERR_TOO_LARGE) return st;
-  ctx->err.clear();
+  WS_TRY(ws_plan_find_local_minima(p, ctx->d_img, nullptr, 0, ctx->d_seed_off, &total));
   WS_TRY(grow(ctx, ctx->d_seeds, ctx->d_seeds_cap, 2 * total));
   if (total) WS_CUDA(ctx, launch_minima_write(ctx->d_img, p->d, p->chunk_counts, ctx->d_seeds, (uint32_t)total, s));
   std::vector<uint32_t> h(2 * std::max<size_t>(total, 1)), hoff(n_img + 1);

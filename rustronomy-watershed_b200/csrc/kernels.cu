@@ -241,6 +241,28 @@ cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_
   return cudaGetLastError();
 }
 
+// (usize, usize) pairs -> u32 pairs; anything outside the image becomes 0xFFFFFFFF so that
+// seed_init flags it (the reference panics on an out-of-bounds seed, lib.rs:1366 / 1676).
+__global__ void __launch_bounds__(256) seeds_convert_kernel(const uint64_t* __restrict__ in,
+                                                            uint32_t* __restrict__ out, size_t n2, uint64_t rows,
+                                                            uint64_t cols) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    const uint64_t v = in[i];
+    const uint64_t lim = (i & 1) ? cols : rows;
+    out[i] = v < lim ? (uint32_t)v : 0xFFFFFFFFu;
+  }
+}
+
+cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseeds, size_t rows, size_t cols,
+                                 cudaStream_t s) {
+  if (nseeds == 0) return cudaSuccess;
+  const size_t n2 = 2 * nseeds;
+  const unsigned grid = (unsigned)min((size_t)148 * 8, (n2 + 255) / 256);
+  seeds_convert_kernel<<<grid, 256, 0, s>>>(in, out, n2, rows, cols);
+  return cudaGetLastError();
+}
+
 struct FloodArgs {
   FloodBuffers b;
   ImageDims d;
@@ -627,19 +649,35 @@ __global__ void __launch_bounds__(256) uf_init_kernel(MergeBuffers m, const uint
                                                       ImageDims d, const uint32_t* __restrict__ seeds_rc,
                                                       const uint32_t* __restrict__ seed_off, uint32_t nseeds) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nseeds) return;
-  m.parent[i] = i;
-  m.hook_to[i] = i;
-  m.hook_lvl[i] = 255;
-  int lo = 0, hi = d.n_img;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
+  int lo = 0;
+  bool present = false;
+  if (i < nseeds) {
+    m.parent[i] = i;
+    m.hook_to[i] = i;
+    m.hook_lvl[i] = 255;
+    int hi = d.n_img;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
+    if (r < (uint32_t)d.rows && c < (uint32_t)d.cols) {
+      const size_t p = (size_t)lo * d.px_per_img() + (size_t)r * d.cols + c;
+      present = (lab[p] & LAB_MASK) == i - __ldg(seed_off + lo) + 1u;
+    }
   }
-  const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
-  if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) return;
-  const size_t p = (size_t)lo * d.px_per_img() + (size_t)r * d.cols + c;
-  if ((lab[p] & LAB_MASK) == i - __ldg(seed_off + lo) + 1u) atomicAdd(&m.ndistinct[lo], 1u);
+  // one atomic per CTA when the whole CTA lies in one slice (seeds are grouped by slice)
+  __shared__ int s_lo[2];
+  if (threadIdx.x == 0) s_lo[0] = lo;
+  if (i == nseeds - 1 || (threadIdx.x == blockDim.x - 1 && i < nseeds)) s_lo[1] = lo;
+  __syncthreads();
+  const bool uniform = (s_lo[0] == s_lo[1]);
+  const int n = __syncthreads_count(present && uniform);
+  if (uniform) {
+    if (threadIdx.x == 0 && n) atomicAdd(&m.ndistinct[s_lo[0]], (uint32_t)n);
+  } else if (present) {
+    atomicAdd(&m.ndistinct[lo], 1u);
+  }
 }
 
 cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,

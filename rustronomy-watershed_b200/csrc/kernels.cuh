@@ -46,6 +46,8 @@ cudaError_t launch_minima_write(const uint8_t* img, ImageDims d, const uint32_t*
 cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, cudaStream_t s);
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
                              uint32_t nseeds, cudaStream_t s);
+cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseeds, size_t rows, size_t cols,
+                                 cudaStream_t s);
 cudaError_t launch_flood(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, int check_overflow,
                          int grid, cudaStream_t s);
 
