@@ -12,7 +12,7 @@ from typing import Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libws_b200.so")
+LIB_PATH = os.environ.get("WS_B200_LIB") or os.path.join(HERE, "libws_b200.so")   # override: debugging builds only
 
 WS_OK = 0
 STATUS_NAMES = {

@@ -22,14 +22,22 @@ constexpr uint32_t HOP_MASK = 0x00FFFFFFu;
 constexpr uint32_t LAB_RESOLVED = 0x80000000u;  // lab word holds a final label, not a pixel index
 constexpr uint32_t LAB_MASK = 0x7FFFFFFFu;
 
-// Flood tile: TILE_W x TILE_H pixels per CTA, each thread owns ROWS_PER_THREAD
-// consecutive rows of one column.
+// Flood tile: TILE_W x TILE_H pixels per CTA; 8 consumer warps + 1 producer warp.
 constexpr int TILE_W = 64;
 constexpr int TILE_H = 32;
 constexpr int ROWS_PER_THREAD = 8;
-constexpr int FLOOD_THREADS = TILE_W * TILE_H / ROWS_PER_THREAD;  // 256
-constexpr int SM_W = TILE_W + 2;
+constexpr int FLOOD_CONSUMERS = TILE_W * TILE_H / ROWS_PER_THREAD;  // 256 threads iterate on the tile
+constexpr int FLOOD_THREADS = FLOOD_CONSUMERS + 32;                 // + the producer warp
+constexpr int SM_W = TILE_W + 3;   // working tile, odd row stride: column-wise and row-wise accesses conflict-free
 constexpr int SM_H = TILE_H + 2;
+constexpr int PIX_W = TILE_W + 4;  // byte row stride of the working image tile (17 words, odd)
+// Padded global layouts so that every tile's box (with halo) is an in-bounds, 16-byte aligned
+// set of rows for the bulk-copy engine:
+//   arrival times: image (r, c) -> Tp[(r + 1) * t_pitch + c + T_PAD_L], t_pitch = tiles_x * TILE_W + 8
+//   image bytes:   image (r, c) -> pix[r * pix_pitch + c],              pix_pitch = tiles_x * TILE_W
+constexpr int T_PAD_L = 4;
+constexpr int STG_W = TILE_W + 8;  // words per staged row: image columns c0-4 .. c0+67
+constexpr int STG_H = TILE_H + 2;
 
 struct ImageDims {
   int n_img;      // slices in the batch
@@ -39,6 +47,14 @@ struct ImageDims {
   __host__ __device__ size_t px_total() const { return px_per_img() * (size_t)n_img; }
   __host__ __device__ int tiles_per_img() const { return tiles_x * tiles_y; }
   __host__ __device__ int tiles_total() const { return tiles_per_img() * n_img; }
+  // padded planes
+  __host__ __device__ int t_pitch() const { return tiles_x * TILE_W + 8; }
+  __host__ __device__ int t_rows() const { return tiles_y * TILE_H + 2; }
+  __host__ __device__ size_t t_plane() const { return (size_t)t_pitch() * t_rows(); }
+  __host__ __device__ size_t t_index(int r, int c) const { return (size_t)(r + 1) * t_pitch() + c + T_PAD_L; }
+  __host__ __device__ int pix_pitch() const { return tiles_x * TILE_W; }
+  __host__ __device__ int pix_rows() const { return tiles_y * TILE_H; }
+  __host__ __device__ size_t pix_plane() const { return (size_t)pix_pitch() * pix_rows(); }
 };
 
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { return __ldcg(p); }

@@ -51,6 +51,7 @@ struct ws_plan {
   size_t uf_cap = 0, edges_cap = 0, rep_cap = 0;
   uint32_t* rep = nullptr;
   int rep_level = -1;
+  uint32_t* T_dense = nullptr;       // lazily made dense copy of the arrival times (diagnostic accessor)
   uint32_t* chunk_counts = nullptr;  // minima scratch
   uint32_t* d_total = nullptr;
   uint32_t* h_ctrl = nullptr;        // pinned mirror of fb.ctrl + scalars
@@ -259,7 +260,8 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   auto alloc = [&](void** ptr, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(ptr, std::max<size_t>(bytes, 16));
   };
-  alloc((void**)&p->fb.T, npx * 4);
+  alloc((void**)&p->fb.T, p->d.t_plane() * n_img * 4);
+  alloc((void**)&p->fb.pix, p->d.pix_plane() * n_img);
   alloc((void**)&p->fb.lab, npx * 4);
   alloc((void**)&p->fb.lvl, npx);
   alloc((void**)&p->fb.lists, ntiles * 3 * 4);
@@ -289,6 +291,8 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaStreamSynchronize(p->ctx->stream);
   if (p->ctx->cached == p) p->ctx->cached = nullptr;
   cudaFree(p->fb.T);
+  cudaFree(p->fb.pix);
+  cudaFree(p->T_dense);
   cudaFree(p->fb.lab);
   cudaFree(p->fb.lvl);
   cudaFree(p->fb.lists);
@@ -391,10 +395,10 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   // hop counters can only overflow when a single slice has more than 2^24 pixels
   const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
   WS_CUDA(ctx, cudaEventRecord(p->ev[0], s));
-  WS_CUDA(ctx, launch_fill_state(p->fb, p->d, s));
+  WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_imgs, cfg->max_water_level, s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[1], s));
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, d_imgs, cfg->max_water_level, check_ovf, ctx->flood_grid, s));
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, ctx->flood_grid, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
   WS_CUDA(ctx, launch_parent(p->fb, p->d, s));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
@@ -447,7 +451,15 @@ extern "C" ws_status ws_memcpy_d2h(ws_ctx* ctx, void* h_dst, const void* d_src, 
   return WS_OK;
 }
 
-extern "C" const uint32_t* ws_plan_arrival_times(const ws_plan* p) { return p ? p->fb.T : nullptr; }
+extern "C" const uint32_t* ws_plan_arrival_times(const ws_plan* cp) {
+  ws_plan* p = const_cast<ws_plan*>(cp);
+  if (!p) return nullptr;  // also after a failed run: the diagnostic is most useful then
+  if (cudaSetDevice(p->ctx->device) != cudaSuccess) return nullptr;
+  if (!p->T_dense && cudaMalloc((void**)&p->T_dense, p->d.px_total() * 4) != cudaSuccess) return nullptr;
+  if (launch_unpad_T(p->fb.T, p->d, p->T_dense, p->ctx->stream) != cudaSuccess) return nullptr;
+  if (cudaStreamSynchronize(p->ctx->stream) != cudaSuccess) return nullptr;
+  return p->T_dense;
+}
 extern "C" const uint32_t* ws_plan_labels(const ws_plan* p) { return p ? p->fb.lab : nullptr; }
 extern "C" const uint8_t* ws_plan_levels(const ws_plan* p) { return p ? p->fb.lvl : nullptr; }
 extern "C" const uint32_t* ws_plan_lake_counts(const ws_plan* p) { return p ? p->mb.counts : nullptr; }

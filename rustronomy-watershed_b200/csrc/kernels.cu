@@ -167,260 +167,7 @@ cudaError_t launch_minima_write(const uint8_t* img, ImageDims d, const uint32_t*
   return cudaGetLastError();
 }
 
-// ===========================================================================
-// K2  flood: arrival times of all water levels in one persistent kernel
-//     (replaces the level loop x 'colouring_loop x find_flooded_px x write-back,
-//      lib.rs:1379-1438 / 1689-1748 and 196-257)
-// ===========================================================================
-
-__global__ void __launch_bounds__(256) fill_state_kernel(uint32_t* __restrict__ T, uint32_t* __restrict__ lab,
-                                                         size_t n) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    __stcg(T + i, T_INF);
-    __stcg(lab + i, 0u);
-  }
-}
-
-cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, cudaStream_t s) {
-  const size_t n = d.px_total();
-  const unsigned grid = (unsigned)min((size_t)148 * 16, (n + 255) / 256);
-  fill_state_kernel<<<grid ? grid : 1, 256, 0, s>>>(b.T, b.lab, n);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (size_t)d.tiles_total(), s);
-  if (e != cudaSuccess) return e;
-  return cudaMemsetAsync(b.ctrl, 0, sizeof(uint32_t) * FC_WORDS, s);
-}
-
-__device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t ntiles, int list, uint32_t tile) {
-  const uint32_t bit = 1u << list;
-  const uint32_t old = atomicOr(&b.flags[tile], bit);
-  if (!(old & bit)) {
-    const uint32_t pos = atomicAdd(&b.ctrl[FC_COUNT0 + list], 1u);
-    st_cg(&b.lists[(size_t)list * ntiles + pos], tile);
-  }
-}
-
-// Colour the starting pixels (lib.rs:1365-1367): T = 0, colour = index + 1, a later
-// duplicate overwrites an earlier one (sequential loop) == the largest index wins.
-__global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDims d,
-                                                        const uint32_t* __restrict__ seeds_rc,
-                                                        const uint32_t* __restrict__ seed_off, uint32_t nseeds) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nseeds) return;
-  // slice of seed i: last b with seed_off[b] <= i
-  int lo = 0, hi = d.n_img;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
-  }
-  const int img = lo;
-  const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
-  if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) {
-    atomicOr(&b.ctrl[FC_ERROR], 1u);
-    return;
-  }
-  const size_t p = (size_t)img * d.px_per_img() + (size_t)r * d.cols + c;
-  st_cg(&b.T[p], 0u);
-  atomicMax(&b.lab[p], LAB_RESOLVED | (i - __ldg(seed_off + img) + 1u));
-  const uint32_t ntiles = (uint32_t)d.tiles_total();
-  const int ty = r / TILE_H, tx = c / TILE_W;
-  const uint32_t tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
-  push_tile(b, ntiles, 0, tile);
-  if (r % TILE_H == 0 && ty > 0) push_tile(b, ntiles, 0, tile - d.tiles_x);
-  if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile(b, ntiles, 0, tile + d.tiles_x);
-  if (c % TILE_W == 0 && tx > 0) push_tile(b, ntiles, 0, tile - 1);
-  if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile(b, ntiles, 0, tile + 1);
-}
-
-cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
-                             uint32_t nseeds, cudaStream_t s) {
-  if (nseeds == 0) return cudaSuccess;
-  seed_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds);
-  return cudaGetLastError();
-}
-
-// (usize, usize) pairs -> u32 pairs; anything outside the image becomes 0xFFFFFFFF so that
-// seed_init flags it (the reference panics on an out-of-bounds seed, lib.rs:1366 / 1676).
-__global__ void __launch_bounds__(256) seeds_convert_kernel(const uint64_t* __restrict__ in,
-                                                            uint32_t* __restrict__ out, size_t n2, uint64_t rows,
-                                                            uint64_t cols) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-    const uint64_t v = in[i];
-    const uint64_t lim = (i & 1) ? cols : rows;
-    out[i] = v < lim ? (uint32_t)v : 0xFFFFFFFFu;
-  }
-}
-
-cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseeds, size_t rows, size_t cols,
-                                 cudaStream_t s) {
-  if (nseeds == 0) return cudaSuccess;
-  const size_t n2 = 2 * nseeds;
-  const unsigned grid = (unsigned)min((size_t)148 * 8, (n2 + 255) / 256);
-  seeds_convert_kernel<<<grid, 256, 0, s>>>(in, out, n2, rows, cols);
-  return cudaGetLastError();
-}
-
-struct FloodArgs {
-  FloodBuffers b;
-  ImageDims d;
-  const uint8_t* img;
-  uint32_t lmax;
-  int check_overflow;
-};
-
-enum { EDGE_UP = 1, EDGE_DOWN = 2, EDGE_LEFT = 4, EDGE_RIGHT = 8 };
-
-// Bring one tile (with its 1-pixel halo staged in shared memory) to its local
-// fixed point, write the changed pixels back and queue the neighbours whose
-// halo changed.
-__device__ __forceinline__ void flood_tile(const FloodArgs& a, uint32_t tile, int cur, int nxt, uint32_t* sT,
-                                           uint32_t* s_edge) {
-  const ImageDims& d = a.d;
-  const int tpi = d.tiles_per_img();
-  const int img = tile / tpi;
-  const int trem = tile - img * tpi;
-  const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
-  const int r0 = ty * TILE_H, c0 = tx * TILE_W;
-  const size_t base = (size_t)img * d.px_per_img();
-  uint32_t* Tg = a.b.T + base;
-
-  // stage T + halo; coalesced along rows.  Out-of-image cells never matter:
-  // only border pixels touch them and border pixels have A = T_INF.
-  for (int i = threadIdx.x; i < SM_H * SM_W; i += FLOOD_THREADS) {
-    const int lr = i / SM_W, lc = i - lr * SM_W;
-    const int r = r0 - 1 + lr, c = c0 - 1 + lc;
-    uint32_t v = T_INF;
-    if (r >= 0 && r < d.rows && c >= 0 && c < d.cols) v = ld_cg(Tg + (size_t)r * d.cols + c);
-    sT[i] = v;
-  }
-  if (threadIdx.x == 0) {
-    *s_edge = 0;
-    atomicAnd(&a.b.flags[tile], ~(1u << cur));
-    atomicAdd(&a.b.ctrl[FC_ACTIVATIONS], 1u);
-  }
-
-  const int lc = threadIdx.x % TILE_W;       // column inside the tile
-  const int g = threadIdx.x / TILE_W;        // row group
-  const int c = c0 + lc;
-  const int rb = r0 + g * ROWS_PER_THREAD;
-  uint32_t A[ROWS_PER_THREAD], t[ROWS_PER_THREAD];
-  const uint8_t* ig = a.img + base;
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    const int r = rb + i;
-    // only window centres flood (lib.rs:220), and only pixels at or below the
-    // last water level (filter (1), lib.rs:224, over levels 0..=max)
-    const bool interior = (r >= 1 && r <= d.rows - 2 && c >= 1 && c <= d.cols - 2);
-    uint32_t v = 255u;
-    if (interior) v = __ldg(ig + (size_t)r * d.cols + c);
-    A[i] = (interior && v <= a.lmax) ? ((v << 24) | 1u) : T_INF;
-  }
-  __syncthreads();
-  uint32_t* col = sT + (g * ROWS_PER_THREAD + 1) * SM_W + lc + 1;  // my first pixel
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i) t[i] = col[i * SM_W];
-
-  uint32_t chg = 0;
-  bool ovf = false;
-  int any;
-  do {
-    const uint32_t up = col[-SM_W];
-    const uint32_t dn = col[ROWS_PER_THREAD * SM_W];
-    uint32_t mlr[ROWS_PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i) mlr[i] = min(col[i * SM_W - 1], col[i * SM_W + 1]);
-    uint32_t it = 0;
-    // downward Gauss-Seidel pass inside the thread's column strip ...
-    uint32_t prev = up;
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-      const uint32_t below = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : dn;
-      const uint32_t n = max(A[i], umin3(mlr[i], prev, below) + 1u);
-      if (n < t[i]) {
-        t[i] = n;
-        it |= 1u << i;
-        ovf |= ((n & HOP_MASK) == 0u);
-      }
-      prev = t[i];
-    }
-    // ... and upward
-    uint32_t nextv = dn;
-#pragma unroll
-    for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
-      const uint32_t above = (i > 0) ? t[i - 1] : up;
-      const uint32_t n = max(A[i], umin3(mlr[i], above, nextv) + 1u);
-      if (n < t[i]) {
-        t[i] = n;
-        it |= 1u << i;
-        ovf |= ((n & HOP_MASK) == 0u);
-      }
-      nextv = t[i];
-    }
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i)
-      if (it & (1u << i)) col[i * SM_W] = t[i];
-    chg |= it;
-    any = (it != 0u);
-  } while (__syncthreads_or(any));
-
-  if (chg) {
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i)
-      if (chg & (1u << i)) st_cg(Tg + (size_t)(rb + i) * d.cols + c, t[i]);
-    uint32_t e = 0;
-    if (lc == 0) e |= EDGE_LEFT;
-    if (lc == TILE_W - 1) e |= EDGE_RIGHT;
-    if (g == 0 && (chg & 1u)) e |= EDGE_UP;
-    if (g == TILE_H / ROWS_PER_THREAD - 1 && (chg & (1u << (ROWS_PER_THREAD - 1)))) e |= EDGE_DOWN;
-    if (e) atomicOr(s_edge, e);
-    if (a.check_overflow && ovf) atomicOr(&a.b.ctrl[FC_ERROR], 2u);
-    __threadfence();
-  }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    const uint32_t e = *s_edge;
-    const uint32_t ntiles = (uint32_t)d.tiles_total();
-    if (threadIdx.x == 0 && (e & EDGE_UP) && ty > 0) push_tile(a.b, ntiles, nxt, tile - d.tiles_x);
-    if (threadIdx.x == 1 && (e & EDGE_DOWN) && ty + 1 < d.tiles_y) push_tile(a.b, ntiles, nxt, tile + d.tiles_x);
-    if (threadIdx.x == 2 && (e & EDGE_LEFT) && tx > 0) push_tile(a.b, ntiles, nxt, tile - 1);
-    if (threadIdx.x == 3 && (e & EDGE_RIGHT) && tx + 1 < d.tiles_x) push_tile(a.b, ntiles, nxt, tile + 1);
-  }
-}
-
-// Persistent cooperative kernel.  Sweep s drains worklist s%3 (tiles handed out
-// through an atomic cursor), fills worklist (s+1)%3 and resets worklist (s+2)%3;
-// one grid barrier per sweep; ends when a sweep starts with an empty list.
-__global__ void __launch_bounds__(FLOOD_THREADS) flood_kernel(FloodArgs a) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ uint32_t sT[SM_H * SM_W];
-  __shared__ uint32_t s_tile, s_edge;
-  const uint32_t ntiles = (uint32_t)a.d.tiles_total();
-  int cur = 0;
-  for (;;) {
-    const uint32_t n = ld_cg(&a.b.ctrl[FC_COUNT0 + cur]);
-    if (n == 0) break;
-    const int nxt = (cur + 1) % 3, old = (cur + 2) % 3;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      st_cg(&a.b.ctrl[FC_COUNT0 + old], 0u);
-      st_cg(&a.b.ctrl[FC_CURSOR0 + old], 0u);
-      atomicAdd(&a.b.ctrl[FC_SWEEPS], 1u);
-    }
-    for (;;) {
-      __syncthreads();
-      if (threadIdx.x == 0) s_tile = atomicAdd(&a.b.ctrl[FC_CURSOR0 + cur], 1u);
-      __syncthreads();
-      const uint32_t k = s_tile;
-      if (k >= n) break;
-      const uint32_t tile = ld_cg(&a.b.lists[(size_t)cur * ntiles + k]);
-      flood_tile(a, tile, cur, nxt, sT, &s_edge);
-    }
-    grid.sync();
-    cur = nxt;
-  }
-}
+// K2 (flood) and the parent-pointer kernel of K3 live in flood.cu.
 
 static int coop_max_grid(const void* fn, int threads, int device) {
   int per_sm = 0, sms = 0;
@@ -429,57 +176,9 @@ static int coop_max_grid(const void* fn, int threads, int device) {
   return per_sm * sms;
 }
 
-int flood_max_grid(int device) { return coop_max_grid((const void*)flood_kernel, FLOOD_THREADS, device); }
-
-cudaError_t launch_flood(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, int check_overflow,
-                         int grid, cudaStream_t s) {
-  FloodArgs a{b, d, img, lmax, check_overflow};
-  void* args[] = {&a};
-  const int want = d.tiles_total();
-  const int g = want < grid ? (want > 0 ? want : 1) : grid;
-  return cudaLaunchCooperativeKernel((const void*)flood_kernel, dim3(g), dim3(FLOOD_THREADS), args, 0, s);
-}
-
 // ===========================================================================
-// K3  labels: parent pointer (the `col0` decision of lib.rs:235-255) + pointer jumping
+// K3  labels: pointer jumping (the parent pointers come from flood.cu)
 // ===========================================================================
-
-__global__ void __launch_bounds__(256) parent_kernel(FloodBuffers b, ImageDims d) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y;
-  const int img = blockIdx.z;
-  if (c >= d.cols) return;
-  const size_t base = (size_t)img * d.px_per_img();
-  const size_t p = base + (size_t)r * d.cols + c;
-  const uint32_t t = b.T[p];
-  b.lvl[p] = (t >= T_INF) ? (uint8_t)255 : (uint8_t)(t >> 24);
-  if (t >= T_INF) {
-    b.lab[p] = LAB_RESOLVED;  // UNCOLOURED
-    return;
-  }
-  if (t == 0u) return;  // seed: coloured by seed_init
-  // A coloured non-seed pixel is interior, so all four neighbours exist.  The coloured
-  // neighbours the reference sees when it colours p are exactly those with T(q) < T(p);
-  // `col0` is the first of them in the order down, right, left, up (lib.rs:190, 245).
-  const size_t q_dn = p + d.cols, q_rt = p + 1, q_lf = p - 1, q_up = p - d.cols;
-  size_t q;
-  if (b.T[q_dn] < t) q = q_dn;
-  else if (b.T[q_rt] < t) q = q_rt;
-  else if (b.T[q_lf] < t) q = q_lf;
-  else if (b.T[q_up] < t) q = q_up;
-  else {
-    atomicOr(&b.ctrl[FC_ERROR], 4u);  // cannot happen at a fixed point
-    b.lab[p] = LAB_RESOLVED;
-    return;
-  }
-  b.lab[p] = (uint32_t)q;
-}
-
-cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s) {
-  dim3 grid((d.cols + 255) / 256, d.rows, d.n_img);
-  parent_kernel<<<grid, 256, 0, s>>>(b, d);
-  return cudaGetLastError();
-}
 
 // Pointer jumping to the seed: lab[p] <- lab[lab[p]] until every word is a resolved label.
 // In-place and racy on purpose: whatever a thread reads is a valid ancestor or the final label.

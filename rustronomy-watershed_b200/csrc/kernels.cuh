@@ -19,7 +19,8 @@ enum FloodCtrl {
 };
 
 struct FloodBuffers {
-  uint32_t* T;       // [px_total] arrival times
+  uint32_t* T;       // [n_img][t_rows][t_pitch] arrival times, padded layout (common.cuh)
+  uint8_t* pix;      // [n_img][pix_rows][pix_pitch] image bytes re-encoded for the flood (255 = never floods)
   uint32_t* lab;     // [px_total] label / parent words
   uint8_t* lvl;      // [px_total] level of colouring
   uint32_t* lists;   // [3][tiles_total] worklists
@@ -43,13 +44,13 @@ cudaError_t launch_minima_write(const uint8_t* img, ImageDims d, const uint32_t*
                                 uint32_t* out_rc, uint32_t cap, cudaStream_t s);
 
 // --- flood (find_flooded_px + write-back over all levels, lib.rs:196-257, 1379-1438) ---
-cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, cudaStream_t s);
+cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, cudaStream_t s);
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
                              uint32_t nseeds, cudaStream_t s);
 cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseeds, size_t rows, size_t cols,
                                  cudaStream_t s);
-cudaError_t launch_flood(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, int check_overflow,
-                         int grid, cudaStream_t s);
+cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int grid, cudaStream_t s);
+cudaError_t launch_unpad_T(const uint32_t* Tp, ImageDims d, uint32_t* out, cudaStream_t s);
 
 // --- labels (colour decision of lib.rs:235-255 with the `col0` tie-break) ---
 cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s);
