@@ -5,9 +5,8 @@
 // where noted):
 //   fill_state -> seed_init -> flood (persistent, cooperative)
 //   -> parent -> jump (persistent, cooperative)                      [labels + levels]
-//   merging only: edge_hist -> edge_scan -> (host reads the edge total, grows the
-//   edge buffer if needed) -> edge_scatter -> uf_init -> union_levels (persistent,
-//   cooperative) -> lake_counts
+//   merging only: merge_reduce (per-tile Kruskal in shared memory) -> red_hist -> edge_scan ->
+//   red_scatter -> uf_init -> union_levels (persistent, cooperative) -> lake_counts
 #include "../../include/ws_b200.h"
 #include "kernels.cuh"
 
@@ -269,6 +268,7 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->fb.ctrl, FC_WORDS * 4);
   alloc((void**)&p->mb.level_hist, 257 * 4);
   alloc((void**)&p->mb.level_cursor, 256 * 4);
+  alloc((void**)&p->mb.red_count, 16);
   alloc((void**)&p->mb.unions, n_img * 256 * 4);
   alloc((void**)&p->mb.ndistinct, n_img * 4);
   alloc((void**)&p->mb.counts, n_img * 256 * 4);
@@ -301,6 +301,9 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->mb.level_hist);
   cudaFree(p->mb.level_cursor);
   cudaFree(p->mb.edges);
+  cudaFree(p->mb.red_ab);
+  cudaFree(p->mb.red_w);
+  cudaFree(p->mb.red_count);
   cudaFree(p->mb.parent);
   cudaFree(p->mb.hook_to);
   cudaFree(p->mb.hook_lvl);
@@ -353,24 +356,25 @@ static ws_status plan_merge(ws_plan* p) {
     WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_lvl, n));
     p->uf_cap = n;
   }
-  WS_CUDA(ctx, launch_edge_hist(p->fb.lab, p->fb.lvl, p->d, p->mb.level_hist, s));
-  WS_CUDA(ctx, launch_edge_scan(p->mb.level_hist, p->mb.level_cursor, s));
-  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.level_hist + 256, 4, cudaMemcpyDeviceToHost, s));
-  WS_CUDA(ctx, cudaStreamSynchronize(s));  // the only mid-pipeline host round trip: size of the edge list
-  const size_t nedges = p->h_ctrl[FC_WORDS + 1];
-  if (nedges > p->edges_cap || !p->mb.edges) {
-    cudaFree(p->mb.edges);
-    p->mb.edges = nullptr; p->edges_cap = 0;
-    const size_t n = std::max<size_t>(nedges + nedges / 8, 1024);
-    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.edges, n * sizeof(uint2)));
-    p->edges_cap = n;
+  // edge buffers: bounded by (nodes per tile - 1) forest edges per tile, so no host round trip is needed
+  const size_t cap = merge_reduce_capacity(p->d);
+  if (cap > p->edges_cap || !p->mb.edges) {
+    cudaFree(p->mb.edges); cudaFree(p->mb.red_ab); cudaFree(p->mb.red_w);
+    p->mb.edges = p->mb.red_ab = nullptr; p->mb.red_w = nullptr; p->edges_cap = 0;
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.red_ab, cap * sizeof(uint2)));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.red_w, cap));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.edges, cap * sizeof(uint2)));
+    p->edges_cap = cap;
   }
-  if (nedges) WS_CUDA(ctx, launch_edge_scatter(p->fb.lab, p->fb.lvl, p->d, p->seed_off, p->mb.level_cursor, p->mb.edges, s));
+  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->seed_off, lmax, p->mb.red_ab, p->mb.red_w,
+                                   p->mb.red_count, s));
+  WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, p->mb.level_hist, p->mb.level_cursor,
+                               p->mb.edges, s));
   WS_CUDA(ctx, launch_uf_init(p->mb, p->fb.lab, p->d, p->seeds, p->seed_off, (uint32_t)p->nseeds, s));
-  if (nedges) WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
+  WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
   WS_CUDA(ctx, launch_lake_counts(p->mb, p->d.n_img, lmax, s));
-  p->stats[3] = nedges;
-  p->stats[4] += 4 + (nedges ? 2 : 0);
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
+  p->stats[4] += 7;
   p->merged = true;
   p->rep_level = -1;
   return WS_OK;
@@ -412,6 +416,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
                                cudaMemcpyDeviceToHost, s));
   WS_CUDA(ctx, cudaStreamSynchronize(s));
   p->stats[0] = p->h_ctrl[FC_SWEEPS];
+  if (p->merged) p->stats[3] = p->h_ctrl[FC_WORDS + 1];
   p->stats[1] = p->h_ctrl[FC_ACTIVATIONS];
   p->stats[2] = p->h_ctrl[FC_JUMP_ROUNDS];
   const uint32_t err = p->h_ctrl[FC_ERROR];

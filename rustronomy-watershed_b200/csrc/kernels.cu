@@ -219,128 +219,9 @@ cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s) {
 }
 
 // ===========================================================================
-// K4  merging: basin adjacency edges bucketed by level + union-find per level
+// K4  merging: the edge reduction lives in merge.cu; union-find over the reduced edges below
 //     (find_merge / make_colour_map / recolour, lib.rs:393-542, 590-592)
-//
-// Two adjacent coloured pixels with different segmenting labels a != b belong to
-// the same lake from level w = max(level(p), level(q)) on, provided at least one
-// of them is a window centre (find_merge only looks from interior pixels,
-// lib.rs:411-414).  Processing the edges in level order with a union-find is the
-// reference's per-level closure; the number of successful unions at level w is
-// the number of lakes that disappear at w.
 // ===========================================================================
-
-struct EdgePair {
-  uint32_t a, b, w;
-  bool ok;
-};
-
-__device__ __forceinline__ bool is_interior(const ImageDims& d, int r, int c) {
-  return r >= 1 && r <= d.rows - 2 && c >= 1 && c <= d.cols - 2;
-}
-
-// edges of pixel (r,c) towards its right (k=0) and lower (k=1) neighbour
-__device__ __forceinline__ void pixel_edges(const uint32_t* __restrict__ lab, const uint8_t* __restrict__ lvl,
-                                            const ImageDims& d, int img, int r, int c, EdgePair e[2]) {
-  e[0].ok = e[1].ok = false;
-  const size_t p = (size_t)img * d.px_per_img() + (size_t)r * d.cols + c;
-  const uint32_t a = lab[p] & LAB_MASK;
-  if (a == 0u) return;
-  const uint32_t la = lvl[p];
-  const bool pin = is_interior(d, r, c);
-  if (c + 1 < d.cols) {
-    const uint32_t bq = lab[p + 1] & LAB_MASK;
-    if (bq != 0u && bq != a && (pin || is_interior(d, r, c + 1))) {
-      e[0].ok = true; e[0].a = a; e[0].b = bq; e[0].w = max(la, (uint32_t)lvl[p + 1]);
-    }
-  }
-  if (r + 1 < d.rows) {
-    const uint32_t bq = lab[p + d.cols] & LAB_MASK;
-    if (bq != 0u && bq != a && (pin || is_interior(d, r + 1, c))) {
-      e[1].ok = true; e[1].a = a; e[1].b = bq; e[1].w = max(la, (uint32_t)lvl[p + d.cols]);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) edge_hist_kernel(const uint32_t* __restrict__ lab,
-                                                        const uint8_t* __restrict__ lvl, ImageDims d,
-                                                        uint32_t* __restrict__ level_hist) {
-  __shared__ uint32_t s_hist[256];
-  s_hist[threadIdx.x] = 0;
-  __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < d.cols) {
-    EdgePair e[2];
-    pixel_edges(lab, lvl, d, blockIdx.z, blockIdx.y, c, e);
-    if (e[0].ok) atomicAdd(&s_hist[e[0].w], 1u);
-    if (e[1].ok) atomicAdd(&s_hist[e[1].w], 1u);
-  }
-  __syncthreads();
-  if (s_hist[threadIdx.x]) atomicAdd(&level_hist[threadIdx.x], s_hist[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(256) edge_scan_kernel(uint32_t* level_hist, uint32_t* level_cursor) {
-  __shared__ uint32_t s[256];
-  s[threadIdx.x] = level_hist[threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < 256; ++i) {
-      const uint32_t v = s[i];
-      s[i] = run;
-      run += v;
-    }
-    level_hist[256] = run;
-  }
-  __syncthreads();
-  level_hist[threadIdx.x] = s[threadIdx.x];
-  level_cursor[threadIdx.x] = s[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(256) edge_scatter_kernel(const uint32_t* __restrict__ lab,
-                                                           const uint8_t* __restrict__ lvl, ImageDims d,
-                                                           const uint32_t* __restrict__ seed_off,
-                                                           uint32_t* __restrict__ level_cursor,
-                                                           uint2* __restrict__ edges) {
-  __shared__ uint32_t s_cnt[256], s_base[256];
-  s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  EdgePair e[2];
-  e[0].ok = e[1].ok = false;
-  uint32_t slot[2] = {0, 0};
-  if (c < d.cols) {
-    pixel_edges(lab, lvl, d, blockIdx.z, blockIdx.y, c, e);
-    if (e[0].ok) slot[0] = atomicAdd(&s_cnt[e[0].w], 1u);
-    if (e[1].ok) slot[1] = atomicAdd(&s_cnt[e[1].w], 1u);
-  }
-  __syncthreads();
-  if (s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(&level_cursor[threadIdx.x], s_cnt[threadIdx.x]);
-  __syncthreads();
-  const uint32_t gbase = __ldg(seed_off + blockIdx.z) - 1u;  // global colour id = seed_off[img] + colour - 1
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-    if (e[k].ok) edges[s_base[e[k].w] + slot[k]] = make_uint2(gbase + e[k].a, gbase + e[k].b);
-}
-
-cudaError_t launch_edge_hist(const uint32_t* lab, const uint8_t* lvl, ImageDims d, uint32_t* level_hist,
-                             cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(level_hist, 0, 257 * sizeof(uint32_t), s);
-  if (e != cudaSuccess) return e;
-  dim3 grid((d.cols + 255) / 256, d.rows, d.n_img);
-  edge_hist_kernel<<<grid, 256, 0, s>>>(lab, lvl, d, level_hist);
-  return cudaGetLastError();
-}
-cudaError_t launch_edge_scan(uint32_t* level_hist, uint32_t* level_cursor, cudaStream_t s) {
-  edge_scan_kernel<<<1, 256, 0, s>>>(level_hist, level_cursor);
-  return cudaGetLastError();
-}
-cudaError_t launch_edge_scatter(const uint32_t* lab, const uint8_t* lvl, ImageDims d, const uint32_t* seed_off,
-                                uint32_t* level_cursor, uint2* edges, cudaStream_t s) {
-  dim3 grid((d.cols + 255) / 256, d.rows, d.n_img);
-  edge_scatter_kernel<<<grid, 256, 0, s>>>(lab, lvl, d, seed_off, level_cursor, edges);
-  return cudaGetLastError();
-}
 
 // union-find initialisation + number of colours actually present on the canvas
 // (a seed position overwritten by a later duplicate seed loses its colour, lib.rs:1365-1367)
@@ -405,9 +286,12 @@ __global__ void __launch_bounds__(256) union_levels_kernel(MergeBuffers m, const
                                                            int n_img, uint32_t lmax) {
   cg::grid_group grid = cg::this_grid();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
+  __shared__ uint32_t s_ok;  // successes of this CTA at the current level (single-slice runs)
   for (uint32_t l = 0; l <= lmax; ++l) {
     const uint32_t lo = __ldg(m.level_hist + l), hi = __ldg(m.level_hist + l + 1);
     if (lo == hi) continue;  // uniform across the grid
+    if (threadIdx.x == 0) s_ok = 0;
+    __syncthreads();
     for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
       const uint2 e = m.edges[i];
       uint32_t a = e.x, b = e.y;
@@ -419,16 +303,22 @@ __global__ void __launch_bounds__(256) union_levels_kernel(MergeBuffers m, const
         if (atomicCAS(m.parent + a, a, b) == a) {
           m.hook_to[a] = b;
           m.hook_lvl[a] = (uint8_t)l;
-          int s0 = 0, s1 = n_img;
-          while (s1 - s0 > 1) {
-            const int mid = (s0 + s1) >> 1;
-            if (__ldg(seed_off + mid) <= a) s0 = mid; else s1 = mid;
+          if (n_img == 1) {
+            atomicAdd(&s_ok, 1u);  // one global atomic per CTA and level instead of one per union
+          } else {
+            int s0 = 0, s1 = n_img;
+            while (s1 - s0 > 1) {
+              const int mid = (s0 + s1) >> 1;
+              if (__ldg(seed_off + mid) <= a) s0 = mid; else s1 = mid;
+            }
+            atomicAdd(&m.unions[(size_t)s0 * 256 + l], 1u);
           }
-          atomicAdd(&m.unions[(size_t)s0 * 256 + l], 1u);
           break;
         }
       }
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_ok) atomicAdd(&m.unions[l], s_ok);
     grid.sync();
   }
 }

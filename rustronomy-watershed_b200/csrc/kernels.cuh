@@ -60,7 +60,10 @@ cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s);
 struct MergeBuffers {
   uint32_t* level_hist;   // [256] edges per level, then exclusive offsets [257]
   uint32_t* level_cursor; // [256]
-  uint2* edges;           // [n_edges] (global colour id a, b), bucketed by level
+  uint2* red_ab;          // [cap] forest edges of the tiles (global colour ids), unsorted
+  uint8_t* red_w;         // [cap] their levels
+  uint32_t* red_count;    // [1]
+  uint2* edges;           // [cap] the same edges bucketed by level
   uint32_t* parent;       // [nseeds] union-find with path halving
   uint32_t* hook_to;      // [nseeds] immutable link written once when a root is hooked
   uint8_t* hook_lvl;      // [nseeds] level of that link, 255 = still a root
@@ -68,12 +71,13 @@ struct MergeBuffers {
   uint32_t* ndistinct;    // [n_img] colours present on the canvas
   uint32_t* counts;       // [n_img][256] lakes per level
 };
-cudaError_t launch_edge_hist(const uint32_t* lab, const uint8_t* lvl, ImageDims d, uint32_t* level_hist,
-                             cudaStream_t s);
-// level_hist[256] -> exclusive offsets in level_hist[0..256], cursors = offsets
-cudaError_t launch_edge_scan(uint32_t* level_hist, uint32_t* level_cursor, cudaStream_t s);
-cudaError_t launch_edge_scatter(const uint32_t* lab, const uint8_t* lvl, ImageDims d, const uint32_t* seed_off,
-                                uint32_t* level_cursor, uint2* edges, cudaStream_t s);
+// per-tile exact Kruskal in shared memory: emits only the tile's spanning-forest edges (merge.cu)
+size_t merge_reduce_capacity(const ImageDims& d);
+cudaError_t launch_merge_reduce(const uint32_t* lab, const uint8_t* lvl, ImageDims d, const uint32_t* seed_off,
+                                uint32_t lmax, uint2* red_ab, uint8_t* red_w, uint32_t* red_count, cudaStream_t s);
+// counting sort of the reduced edges by level: level_hist[0..256] = exclusive offsets, edges = buckets
+cudaError_t launch_red_sort(const uint2* red_ab, const uint8_t* red_w, const uint32_t* red_count,
+                            uint32_t* level_hist, uint32_t* level_cursor, uint2* edges, cudaStream_t s);
 cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,
                            const uint32_t* seed_off, uint32_t nseeds, cudaStream_t s);
 cudaError_t launch_union_levels(MergeBuffers m, const uint32_t* seed_off, int n_img, uint32_t lmax, int grid,
