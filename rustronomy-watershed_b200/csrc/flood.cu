@@ -265,7 +265,7 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) {
         const uint32_t nb = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : dn;
-        const uint32_t n = max(Ac[i], umin3(m[i], prev, nb) + 1u);
+        const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ac[i]);  // max(A, 1 + min3)
         if (n < t[i]) { t[i] = n; it |= 1u << i; ovf |= ((n & HOP_MASK) == 0u); }
         prev = t[i];
       }
@@ -273,7 +273,7 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
 #pragma unroll
       for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
         const uint32_t nb = (i > 0) ? t[i - 1] : up;
-        const uint32_t n = max(Ac[i], umin3(m[i], prev, nb) + 1u);
+        const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ac[i]);  // max(A, 1 + min3)
         if (n < t[i]) { t[i] = n; it |= 1u << i; ovf |= ((n & HOP_MASK) == 0u); }
         prev = t[i];
       }
@@ -294,7 +294,7 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
 #pragma unroll
       for (int i = 0; i < ROWS_PER_THREAD; ++i) {
         const uint32_t nb = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : rt;
-        const uint32_t n = max(Ar[i], umin3(m[i], prev, nb) + 1u);
+        const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ar[i]);
         if (n < t[i]) { t[i] = n; it |= 1u << i; ovf |= ((n & HOP_MASK) == 0u); }
         prev = t[i];
       }
@@ -302,7 +302,7 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
 #pragma unroll
       for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
         const uint32_t nb = (i > 0) ? t[i - 1] : lf;
-        const uint32_t n = max(Ar[i], umin3(m[i], prev, nb) + 1u);
+        const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ar[i]);
         if (n < t[i]) { t[i] = n; it |= 1u << i; ovf |= ((n & HOP_MASK) == 0u); }
         prev = t[i];
       }
