@@ -155,6 +155,22 @@ ws_status ws_transform_with_hook(ws_ctx *ctx, const ws_config *cfg,
                                  const ws_image *img, const uint64_t *seeds_rc,
                                  size_t nseeds, ws_level_hook hook, void *user);
 
+/* ---- WatershedUtils::pre_processor / pre_processor_with_max (lib.rs:1081-1173) -- */
+typedef enum ws_dtype {
+  WS_F32 = 0, WS_F64 = 1, WS_I32 = 2, WS_U16 = 3, WS_I16 = 4, WS_U8 = 5, WS_I64 = 6
+} ws_dtype;
+/* `n` elements of a standard-layout array of any dimension -> u8, exactly as the reference does it:
+ * min/max folded from ZERO over the finite values (1147-1156); only values whose f64 image
+ * `is_normal()` (1161) are scaled to [0, max] with truncation (1163-1164), so 0.0 and subnormals
+ * become NEVER_FILL like NaN and -inf (1168-1170); +inf becomes ALWAYS_FILL (1165-1167).
+ * max_value: 1..=254 (`MAX` of pre_processor_with_max, asserted at 1143-1144; pre_processor uses
+ * NORMAL_MAX).  Host pointers.                                                              */
+ws_status ws_pre_processor(ws_ctx *ctx, ws_dtype dtype, const void *data, size_t n,
+                           uint8_t max_value, uint8_t *out);
+/* Same with device pointers (enqueued on the ctx stream, returns without synchronising). */
+ws_status ws_dev_pre_processor(ws_ctx *ctx, ws_dtype dtype, const void *d_data, size_t n,
+                               uint8_t max_value, uint8_t *d_out);
+
 /* ---- compact results (extensions; same computation, smaller outputs) ------ */
 /* Per level: number of lakes (distinct non-zero labels) and of uncoloured
  * pixels -- what a caller derives from transform_to_list, without the

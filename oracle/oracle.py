@@ -83,6 +83,9 @@ def lib():
             C.c_void_p, C.c_void_p]
         L.orc_merging_transform_const.restype = None
         L.orc_merging_transform_const.argtypes = [C.c_size_t, C.c_size_t, C.c_void_p]
+        for f in (L.orc_pre_processor_f64, L.orc_pre_processor_f32, L.orc_pre_processor_i64):
+            f.restype = C.c_int
+            f.argtypes = [C.c_void_p, C.c_size_t, C.c_uint8, C.c_void_p]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -177,6 +180,26 @@ def find_lake_sizes(colours) -> np.ndarray:
 def merging_transform_const(rows: int, cols: int) -> np.ndarray:
     out = np.empty((rows, cols), dtype=np.uint64)
     lib().orc_merging_transform_const(rows, cols, _p(out))
+    return out
+
+
+def pre_processor(img, max_value: int = NORMAL_MAX) -> np.ndarray:
+    """lib.rs:1081-1173 (pre_processor = pre_processor_with_max::<NORMAL_MAX>)."""
+    a = np.ascontiguousarray(img)
+    if a.dtype == np.float64:
+        fn, b = lib().orc_pre_processor_f64, a
+    elif a.dtype == np.float32:
+        fn, b = lib().orc_pre_processor_f32, a
+    elif np.issubdtype(a.dtype, np.integer):
+        fn, b = lib().orc_pre_processor_i64, np.ascontiguousarray(a, dtype=np.int64)
+    else:
+        raise TypeError(a.dtype)
+    out = np.empty(a.shape, dtype=np.uint8)
+    rc = fn(_p(b), b.size, max_value, _p(out))
+    if rc == -1:
+        raise AssertionError("MAX must satisfy ALWAYS_FILL < MAX < NEVER_FILL (lib.rs:1143-1144)")
+    if rc != 0:
+        raise ValueError("to_u8() failed (the reference would panic on unwrap, lib.rs:1164)")
     return out
 
 

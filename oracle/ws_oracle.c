@@ -10,6 +10,7 @@
  */
 #include "ws_oracle.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -553,3 +554,42 @@ void orc_merging_transform_const(size_t rows, size_t cols, uint64_t *out) {
   for (size_t r = 1; r + 1 < rows; ++r)
     for (size_t c = 1; c + 1 < cols; ++c) out[r * cols + c] = 123;
 }
+
+/* ------------------------------------------------------------------------ */
+/* pre_processor_with_max  (lib.rs:1134-1173)                               */
+/* ------------------------------------------------------------------------ */
+
+static int pp_map(double f, double min, double max, uint8_t maxv, uint8_t *out) {
+  if (isnormal(f)) { /* lib.rs:1161 */
+    const volatile double normal = (f - min) / (max - min); /* lib.rs:1163 */
+    const volatile double scaled = normal * (double)maxv;   /* lib.rs:1164 */
+    /* ToPrimitive::to_u8 on f64: Some(truncated) iff -1 < x < 256 */
+    if (!(scaled > -1.0 && scaled < 256.0)) return -2;
+    *out = (uint8_t)scaled;
+  } else if (isinf(f) && !signbit(f)) {
+    *out = ORC_ALWAYS_FILL; /* lib.rs:1165-1167 */
+  } else {
+    *out = ORC_NEVER_FILL; /* lib.rs:1168-1170 */
+  }
+  return 0;
+}
+
+#define ORC_PP_IMPL(NAME, T)                                                     \
+  int NAME(const T *in, size_t n, uint8_t maxv, uint8_t *out) {                  \
+    if (!(maxv < ORC_NEVER_FILL) || !(maxv > ORC_ALWAYS_FILL)) return -1;        \
+    T mn = (T)0, mx = (T)0; /* fold(T::zero(), ..), lib.rs:1147-1156 */          \
+    for (size_t i = 0; i < n; ++i) {                                             \
+      const double f = (double)in[i];                                            \
+      if (in[i] < mn && isfinite(f)) mn = in[i];                                 \
+      if (in[i] > mx && isfinite(f)) mx = in[i];                                 \
+    }                                                                            \
+    for (size_t i = 0; i < n; ++i) {                                             \
+      const int rc = pp_map((double)in[i], (double)mn, (double)mx, maxv, &out[i]); \
+      if (rc) return rc;                                                         \
+    }                                                                            \
+    return 0;                                                                    \
+  }
+
+ORC_PP_IMPL(orc_pre_processor_f64, double)
+ORC_PP_IMPL(orc_pre_processor_f32, float)
+ORC_PP_IMPL(orc_pre_processor_i64, int64_t)

@@ -112,6 +112,15 @@ int orc_transform_with_hook(int kind, const uint8_t *img, size_t rows,
 /* src/lib.rs:1524-1536: constant image, interior 123, border 0.              */
 void orc_merging_transform_const(size_t rows, size_t cols, uint64_t *out);
 
+/* src/lib.rs:1134-1173 pre_processor_with_max (pre_processor = MAX 254, lib.rs:1086), for
+ * f64 / f32 / i64 element types.  min and max are folded from zero over the finite values,
+ * compared in the element type (1147-1156); a value is scaled only if its f64 image is_normal()
+ * (1161); +inf -> ALWAYS_FILL (1165-1167), everything else -> NEVER_FILL (1168-1170).
+ * Returns -1 if MAX is not in 1..=254 (the asserts at 1143-1144), -2 if to_u8() would fail.   */
+int orc_pre_processor_f64(const double *in, size_t n, uint8_t max, uint8_t *out);
+int orc_pre_processor_f32(const float *in, size_t n, uint8_t max, uint8_t *out);
+int orc_pre_processor_i64(const int64_t *in, size_t n, uint8_t max, uint8_t *out);
+
 /* Number of OpenMP threads the sweeps will use (1 if built without OpenMP).  */
 int orc_num_threads(void);
 void orc_set_num_threads(int n);

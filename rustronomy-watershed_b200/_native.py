@@ -66,6 +66,8 @@ SIGNATURES = {
     "ws_transform_batch": (C.c_int, [_P, C.POINTER(WsConfig), _P, C.c_size_t, C.c_size_t, C.c_size_t,
                                      _P, _P, _P, _P]),
     "ws_find_local_minima_batch": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(_P), _P]),
+    "ws_pre_processor": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_uint8, _P]),
+    "ws_dev_pre_processor": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_uint8, _P]),
     "ws_ctx_stream": (_P, [_P]),
     "ws_ctx_synchronize": (C.c_int, [_P]),
     "ws_plan_create": (C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(_P)]),

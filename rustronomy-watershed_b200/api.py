@@ -117,12 +117,35 @@ class TransformBuilder(Generic[T]):
 
 
 class WatershedUtils:
-    """lib.rs:1069-1198 (pre_processor is listed as "next" in SURVEY.md section 8(f))."""
+    """lib.rs:1069-1198."""
 
     device = 0
 
     def _ctx(self) -> N.Context:
         return N.default_context(self.device)
+
+    _DTYPES = {"float32": 0, "float64": 1, "int32": 2, "uint16": 3, "int16": 4, "uint8": 5, "int64": 6}
+
+    def pre_processor(self, img: np.ndarray) -> np.ndarray:
+        """lib.rs:1081-1087: any numeric array (any dimension) -> u8 in [0, NORMAL_MAX]."""
+        return self.pre_processor_with_max(img, NORMAL_MAX)
+
+    def pre_processor_with_max(self, img: np.ndarray, MAX: int) -> np.ndarray:
+        """lib.rs:1134-1173.  Raises AssertionError like the reference's asserts (1143-1144)."""
+        a = np.asarray(img)
+        code = self._DTYPES.get(a.dtype.name)
+        if code is None:
+            raise TypeError(f"unsupported element type {a.dtype}")
+        if not 0 <= int(MAX) <= 255:
+            raise OverflowError("MAX is a u8")
+        a = np.ascontiguousarray(a)
+        out = np.empty(a.shape, dtype=np.uint8)
+        ctx = self._ctx()
+        st = ctx.lib.ws_pre_processor(ctx.handle, code, a.ctypes.data, a.size, int(MAX), out.ctypes.data)
+        if st in (N.WS_ERR_MAX_TOO_HIGH, N.WS_ERR_MAX_TOO_LOW):
+            raise AssertionError("MAX must satisfy ALWAYS_FILL < MAX < NEVER_FILL")
+        ctx.check(st)
+        return out
 
     def find_local_minima(self, img: np.ndarray) -> np.ndarray:
         """Interior pixels strictly greater than all 8 neighbours, row-major, as an

@@ -36,6 +36,7 @@ struct ws_ctx {
   uint8_t* d_raw = nullptr;   size_t d_raw_cap = 0;
   uint32_t* d_seeds = nullptr; size_t d_seeds_cap = 0;  // [cap][2]
   uint64_t* d_seeds64 = nullptr; size_t d_seeds64_cap = 0;  // staging of the caller's (usize, usize) pairs
+  void* d_pp_scratch = nullptr;  // pre_processor partial minima / maxima
   uint32_t* d_seed_off = nullptr; size_t d_seed_off_cap = 0;
   uint64_t* d_out[2] = {nullptr, nullptr}; size_t d_out_cap[2] = {0, 0};
   uint64_t* h_pin[2] = {nullptr, nullptr}; size_t h_pin_cap[2] = {0, 0};
@@ -215,6 +216,7 @@ extern "C" void ws_ctx_destroy(ws_ctx* c) {
   cudaFree(c->d_raw);
   cudaFree(c->d_seeds);
   cudaFree(c->d_seeds64);
+  cudaFree(c->d_pp_scratch);
   cudaFree(c->d_seed_off);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->d_out[i]);
@@ -668,6 +670,59 @@ ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint6
 }
 
 }  // namespace
+
+static size_t dtype_size(int dtype) {
+  switch (dtype) {
+    case WS_F32: case WS_I32: return 4;
+    case WS_F64: case WS_I64: return 8;
+    case WS_U16: case WS_I16: return 2;
+    case WS_U8: return 1;
+  }
+  return 0;
+}
+
+extern "C" ws_status ws_dev_pre_processor(ws_ctx* ctx, ws_dtype dtype, const void* d_data, size_t n, uint8_t max_value,
+                                          uint8_t* d_out) {
+  if (!ctx || (n && (!d_data || !d_out))) return WS_ERR_INVALID_ARG;
+  if (dtype_size(dtype) == 0) return fail(ctx, WS_ERR_INVALID_ARG, "unknown dtype");
+  // lib.rs:1143-1144: assert!(MAX < NEVER_FILL); assert!(MAX > ALWAYS_FILL)
+  if (max_value >= WS_NEVER_FILL) return fail(ctx, WS_ERR_MAX_TOO_HIGH, ws_status_str(WS_ERR_MAX_TOO_HIGH));
+  if (max_value <= WS_ALWAYS_FILL) return fail(ctx, WS_ERR_MAX_TOO_LOW, ws_status_str(WS_ERR_MAX_TOO_LOW));
+  if (n == 0) return WS_OK;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->d_pp_scratch) WS_CUDA(ctx, cudaMalloc(&ctx->d_pp_scratch, pre_processor_scratch_bytes() + 64));
+  double* minmax = (double*)((char*)ctx->d_pp_scratch + pre_processor_scratch_bytes());
+  WS_CUDA(ctx, launch_pre_processor((int)dtype, d_data, n, max_value, ctx->d_pp_scratch, minmax, d_out, ctx->stream));
+  return WS_OK;
+}
+
+extern "C" ws_status ws_pre_processor(ws_ctx* ctx, ws_dtype dtype, const void* data, size_t n, uint8_t max_value,
+                                      uint8_t* out) {
+  if (!ctx || (n && (!data || !out))) return WS_ERR_INVALID_ARG;
+  const size_t es = dtype_size(dtype);
+  if (es == 0) return fail(ctx, WS_ERR_INVALID_ARG, "unknown dtype");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* d_in = nullptr;
+  uint8_t* d_out = nullptr;
+  cudaError_t e = cudaMalloc(&d_in, std::max<size_t>(n * es, 16));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, std::max<size_t>(n, 16));
+  ws_status st = WS_OK;
+  if (e != cudaSuccess) st = cuda_fail(ctx, e, "ws_pre_processor: cudaMalloc");
+  if (st == WS_OK && n) {
+    e = cudaMemcpyAsync(d_in, data, n * es, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) st = cuda_fail(ctx, e, "ws_pre_processor: upload");
+  }
+  if (st == WS_OK) st = ws_dev_pre_processor(ctx, dtype, d_in, n, max_value, d_out);
+  if (st == WS_OK && n) {
+    e = cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) st = cuda_fail(ctx, e, "ws_pre_processor: download");
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  return st;
+}
 
 extern "C" ws_status ws_find_local_minima_batch(ws_ctx* ctx, const uint8_t* imgs, size_t n_img, size_t rows,
                                                 size_t cols, uint64_t** out_rc, uint64_t* out_offsets) {

@@ -551,3 +551,131 @@ cudaError_t launch_pad_image(const uint8_t* src, int rows, int cols, uint8_t* ds
 }
 
 }  // namespace ws
+
+// ===========================================================================
+// K8  pre_processor / pre_processor_with_max  (lib.rs:1081-1173)
+//
+// Any numeric array -> u8, with the reference's exact behaviour:
+//   min / max are folded from ZERO over the finite values (lib.rs:1147-1156), compared in T;
+//   a value maps through ((x - min) / (max - min)) * MAX, truncated (lib.rs:1163-1164), only if
+//   its f64 image `is_normal()` (lib.rs:1161) -- so 0.0 and subnormals take the else branches;
+//   +inf -> ALWAYS_FILL (lib.rs:1165-1167; the comment there says "negative infinity", the test
+//   `!is_sign_negative()` selects the positive one); everything else (NaN, -inf, 0, subnormal)
+//   -> NEVER_FILL (lib.rs:1168-1170).
+// f64 arithmetic with explicit round-to-nearest operations (no FMA contraction) so the bytes
+// equal the CPU's.
+// ===========================================================================
+namespace ws {
+
+template <typename T>
+__device__ __forceinline__ double pp_to_f64(T v) { return (double)v; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) pp_minmax_kernel(const T* __restrict__ in, size_t n, T* __restrict__ part_min,
+                                                        T* __restrict__ part_max) {
+  __shared__ T s_min[256], s_max[256];
+  T mn = (T)0, mx = (T)0;  // the fold starts at T::zero()
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const T x = in[i];
+    const double f = pp_to_f64(x);
+    const bool fin = !(isinf(f) || isnan(f));
+    if (x < mn && fin) mn = x;
+    if (x > mx && fin) mx = x;
+  }
+  s_min[threadIdx.x] = mn;
+  s_max[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) {
+      if (s_min[threadIdx.x + o] < s_min[threadIdx.x]) s_min[threadIdx.x] = s_min[threadIdx.x + o];
+      if (s_max[threadIdx.x + o] > s_max[threadIdx.x]) s_max[threadIdx.x] = s_max[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part_min[blockIdx.x] = s_min[0];
+    part_max[blockIdx.x] = s_max[0];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pp_finish_kernel(const T* __restrict__ part_min, const T* __restrict__ part_max,
+                                                        int nparts, double* __restrict__ minmax) {
+  __shared__ T s_min[256], s_max[256];
+  T mn = (T)0, mx = (T)0;
+  for (int i = threadIdx.x; i < nparts; i += 256) {
+    if (part_min[i] < mn) mn = part_min[i];
+    if (part_max[i] > mx) mx = part_max[i];
+  }
+  s_min[threadIdx.x] = mn;
+  s_max[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) {
+      if (s_min[threadIdx.x + o] < s_min[threadIdx.x]) s_min[threadIdx.x] = s_min[threadIdx.x + o];
+      if (s_max[threadIdx.x + o] > s_max[threadIdx.x]) s_max[threadIdx.x] = s_max[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    minmax[0] = pp_to_f64(s_min[0]);
+    minmax[1] = pp_to_f64(s_max[0]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pp_map_kernel(const T* __restrict__ in, size_t n, const double* __restrict__ minmax,
+                                                     double maxv, uint8_t* __restrict__ out) {
+  const double mn = minmax[0], range = __dsub_rn(minmax[1], minmax[0]);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double f = pp_to_f64(in[i]);
+    uint8_t v;
+    const double a = fabs(f);
+    const bool normal = a >= 2.2250738585072014e-308 && !isinf(f) && !isnan(f);  // f64::is_normal
+    if (normal) {
+      const double nv = __dmul_rn(__ddiv_rn(__dsub_rn(f, mn), range), maxv);
+      v = (uint8_t)(int)nv;  // truncation towards zero; nv is in [0, MAX]
+    } else if (isinf(f) && f > 0.0) {
+      v = 0;    // ALWAYS_FILL
+    } else {
+      v = 255;  // NEVER_FILL
+    }
+    out[i] = v;
+  }
+}
+
+template <typename T>
+static cudaError_t pp_run(const void* in, size_t n, uint32_t maxv, void* scratch, double* minmax, uint8_t* out,
+                          cudaStream_t s) {
+  const int parts = 1024;
+  T* pmin = (T*)scratch;
+  T* pmax = pmin + parts;
+  pp_minmax_kernel<T><<<parts, 256, 0, s>>>((const T*)in, n, pmin, pmax);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  pp_finish_kernel<T><<<1, 256, 0, s>>>(pmin, pmax, parts, minmax);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  pp_map_kernel<T><<<148 * 8, 256, 0, s>>>((const T*)in, n, minmax, (double)maxv, out);
+  return cudaGetLastError();
+}
+
+size_t pre_processor_scratch_bytes() { return 2 * 1024 * 8; }
+
+cudaError_t launch_pre_processor(int dtype, const void* in, size_t n, uint32_t maxv, void* scratch, double* minmax,
+                                 uint8_t* out, cudaStream_t s) {
+  switch (dtype) {
+    case 0: return pp_run<float>(in, n, maxv, scratch, minmax, out, s);
+    case 1: return pp_run<double>(in, n, maxv, scratch, minmax, out, s);
+    case 2: return pp_run<int32_t>(in, n, maxv, scratch, minmax, out, s);
+    case 3: return pp_run<uint16_t>(in, n, maxv, scratch, minmax, out, s);
+    case 4: return pp_run<int16_t>(in, n, maxv, scratch, minmax, out, s);
+    case 5: return pp_run<uint8_t>(in, n, maxv, scratch, minmax, out, s);
+    case 6: return pp_run<long long>(in, n, maxv, scratch, minmax, out, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace ws

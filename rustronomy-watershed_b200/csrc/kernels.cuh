@@ -109,4 +109,9 @@ cudaError_t launch_fill_const123(uint64_t* out, int rows, int cols, cudaStream_t
 // edge correction (lib.rs:1340-1356): copy into a zeroed canvas one pixel larger on every side
 cudaError_t launch_pad_image(const uint8_t* src, int rows, int cols, uint8_t* dst, cudaStream_t s);
 
+// pre_processor (lib.rs:1081-1173): dtype 0 f32, 1 f64, 2 i32, 3 u16, 4 i16, 5 u8, 6 i64
+size_t pre_processor_scratch_bytes();
+cudaError_t launch_pre_processor(int dtype, const void* in, size_t n, uint32_t maxv, void* scratch, double* minmax,
+                                 uint8_t* out, cudaStream_t s);
+
 }  // namespace ws

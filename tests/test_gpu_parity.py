@@ -285,3 +285,37 @@ def test_medium_fields_against_oracle(ws, oracle):
         refm = oracle.transform(oracle.MERGING, img, seeds, want_sizes=True)
         assert lakes.tolist() == [int((s[1:] != 0).sum()) for s in refm.sizes]
         assert unc.tolist() == [int(s[0]) for s in refm.sizes]
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "int32", "uint16", "int16", "uint8", "int64"])
+def test_pre_processor_bit_exact(ws, oracle, dtype):
+    """lib.rs:1081-1173 incl. its quirks (0 and subnormals -> 255, +inf -> 0, folds from zero)."""
+    rng = np.random.default_rng(11)
+    t = ws.TransformBuilder.default().build_segmenting()
+    if dtype.startswith("float"):
+        x = (rng.normal(size=(301, 517)) * 37.0).astype(dtype)
+        x[rng.random(x.shape) < 0.03] = np.nan
+        x[rng.random(x.shape) < 0.01] = 0.0
+        x[1, 2], x[3, 4], x[5, 6] = np.inf, -np.inf, np.finfo(dtype).tiny / 4
+        cube = (rng.poisson(0.85, size=(7, 40, 50)).astype(dtype))        # tests/integration.rs:189 style
+    else:
+        info = np.iinfo(dtype)
+        x = rng.integers(max(info.min, -5000), min(info.max, 5000), size=(301, 517)).astype(dtype)
+        cube = rng.integers(0, 100, size=(7, 40, 50)).astype(dtype)
+    for arr in (x, cube, x[:1, :1], np.abs(x) + 1):
+        assert np.array_equal(t.pre_processor(arr), oracle.pre_processor(arr))
+    assert np.array_equal(t.pre_processor_with_max(x, 127), oracle.pre_processor(x, 127))
+    for bad in (0, 255):
+        with pytest.raises(AssertionError):
+            t.pre_processor_with_max(x, bad)
+
+
+def test_pre_processor_feeds_transform(ws, oracle):
+    """README-style pipeline on real-valued data: pre_processor -> find_local_minima -> transform."""
+    rng = np.random.default_rng(5)
+    raw = rng.poisson(0.85, size=(200, 220)).astype(np.float64) + rng.normal(size=(200, 220))
+    t = ws.TransformBuilder.default().build_segmenting()
+    img = t.pre_processor(raw)
+    assert np.array_equal(img, oracle.pre_processor(raw))
+    seeds = t.find_local_minima(img)
+    assert np.array_equal(t.transform(img, seeds), oracle.transform(oracle.SEGMENTING, img, seeds).final)

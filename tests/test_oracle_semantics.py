@@ -84,3 +84,37 @@ def test_seed_out_of_bounds_is_an_error(oracle):
 def test_merging_transform_const(oracle):
     out = oracle.merging_transform_const(5, 6)
     assert out[0].sum() == 0 and out[:, 0].sum() == 0 and (out[1:-1, 1:-1] == 123).all()
+
+
+def _pp_numpy(a, MAX=254):
+    """Independent statement of lib.rs:1134-1173 in numpy (f64 arithmetic)."""
+    f = a.astype(np.float64)
+    fin = np.isfinite(f)
+    mn = min(0.0, float(f[fin].min())) if fin.any() else 0.0
+    mx = max(0.0, float(f[fin].max())) if fin.any() else 0.0
+    out = np.full(a.shape, 255, np.uint8)
+    normal = fin & (np.abs(f) >= np.finfo(np.float64).tiny)
+    with np.errstate(all="ignore"):
+        out[normal] = (((f[normal] - mn) / (mx - mn)) * MAX).astype(np.uint8)
+    out[np.isposinf(f)] = 0
+    return out
+
+
+def test_pre_processor_quirks(oracle):
+    """lib.rs:1147-1170: folds start at zero, 0.0 / subnormal / NaN / -inf -> 255, +inf -> 0."""
+    a = np.array([[0.0, 1.0, -2.0, np.nan, np.inf, -np.inf, 5e-324, 3.5]])
+    assert oracle.pre_processor(a).tolist() == [[255, 138, 0, 255, 0, 255, 255, 254]]
+    assert oracle.pre_processor(np.array([5.0, 10.0])).tolist() == [127, 254]      # min folded from 0, not 5
+    assert oracle.pre_processor(np.array([0, 1, -2, 7, 3])).tolist() == [255, 84, 0, 254, 141]
+    assert oracle.pre_processor(np.array([1.0, 2.0]), 127).tolist() == [63, 127]
+    rng = np.random.default_rng(3)
+    for dt in (np.float64, np.float32):
+        x = rng.normal(size=(57, 33)).astype(dt)
+        x[rng.random(x.shape) < 0.05] = np.nan
+        x[3, 4], x[5, 6], x[7, 8] = np.inf, -np.inf, 0.0
+        assert np.array_equal(oracle.pre_processor(x), _pp_numpy(x))
+        assert np.array_equal(oracle.pre_processor(x, 99), _pp_numpy(x, 99))
+    with pytest.raises(AssertionError):
+        oracle.pre_processor(a, 255)
+    with pytest.raises(AssertionError):
+        oracle.pre_processor(a, 0)
