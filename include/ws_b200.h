@@ -244,6 +244,45 @@ ws_status ws_plan_snapshot(ws_plan *plan, ws_kind kind, size_t i, uint8_t level,
  * [2] pointer-jumping rounds, [3] merge edges, [4] kernels launched.          */
 ws_status ws_plan_stats(ws_plan *plan, uint64_t out[8]);
 
+/* ---- one large field as row strips over several plans / GPUs --------------
+ * The arrival-time fixed point does not depend on the decomposition, so strips stay bit-exact.
+ * Each strip is a plan over rows [row_offset, row_offset + rows) of the field INCLUDING one halo
+ * row per neighbouring strip; the caller moves boundary rows between strips (NCCL send/recv over
+ * NVLink, or plain device copies when the strips share a GPU) and loops until nothing changes.
+ * rustronomy-watershed_b200/strips.py is that driver.                                          */
+typedef struct ws_strip {
+  size_t global_rows;    /* rows of the whole field                                            */
+  size_t row_offset;     /* field row of this plan's row 0                                     */
+  uint8_t halo_top;      /* 1: row 0 is a copy of the upper neighbour's last owned row         */
+  uint8_t halo_bottom;   /* 1: the last row is a copy of the lower neighbour's first owned row */
+  uint32_t colour_base;  /* colour of this strip's seed i = colour_base + i + 1                */
+} ws_strip;
+/* State init, seeds of the OWNED rows (plan-local coordinates), local flood to its fixed point.  */
+ws_status ws_plan_strip_begin(ws_plan *plan, const ws_config *cfg, const ws_strip *strip,
+                              const uint8_t *d_img, const uint32_t *d_seeds_rc, size_t nseeds);
+/* Arrival times of the first / last owned row (cols uint32 each; NULL = not wanted).             */
+ws_status ws_plan_strip_export_times(ws_plan *plan, uint32_t *d_top, uint32_t *d_bottom);
+/* Min-merge the neighbours' rows into the halo rows and re-run the local flood from the tiles that
+ * saw a lower value.  *changed = 1 if a halo value got lower.                                    */
+ws_status ws_plan_strip_import_times(ws_plan *plan, const uint32_t *d_top, const uint32_t *d_bottom,
+                                 int *changed);
+/* Parent pointers + pointer jumping inside the strip; halo pixels stay pending.                 */
+ws_status ws_plan_strip_labels(ws_plan *plan);
+/* Label words of the first / last owned row (bit 31 set = resolved label).                       */
+ws_status ws_plan_strip_export_labels(ws_plan *plan, uint32_t *d_top, uint32_t *d_bottom);
+/* Take the neighbours' resolved labels for the halo rows, jump again; *pending = owned pixels
+ * still unresolved (loop over export / exchange / import until it is 0 on every strip).          */
+ws_status ws_plan_strip_import_labels(ws_plan *plan, const uint32_t *d_top, const uint32_t *d_bottom,
+                                      size_t *pending);
+/* Spanning-forest edges of the strip's tiles as (colour a - 1, colour b - 1) uint32 pairs + a
+ * level byte each (device pointers owned by the plan), and the number of this strip's colours
+ * that are present on the canvas.                                                               */
+ws_status ws_plan_strip_edges(ws_plan *plan, const void **d_ab, const void **d_w, size_t *n,
+                              uint32_t *ndistinct);
+/* Kruskal over an edge list gathered from all strips: fills ws_plan_lake_counts()[0..255].      */
+ws_status ws_plan_union_edges(ws_plan *plan, const void *d_ab, const void *d_w, size_t n,
+                              size_t ncolours, uint32_t ndistinct, uint8_t max_water_level);
+
 /* CUDA-event durations (ms) of the phases of the last run, measured on the ctx stream:
  * [0] state fill + seed colouring, [1] flood kernel, [2] parent + pointer jumping,
  * [3] merging (edges, union-find, counts; 0 for segmenting runs).            */
@@ -256,6 +295,7 @@ ws_status ws_dev_free(ws_ctx *ctx, void *d_ptr);
  * after the copy has completed.                                               */
 ws_status ws_memcpy_h2d(ws_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 ws_status ws_memcpy_d2h(ws_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+ws_status ws_memcpy_d2d(ws_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);
 
 #ifdef __cplusplus
 }

@@ -21,3 +21,5 @@ __all__ = [
     "SegmentingWatershed", "TransformBuilder", "Watershed", "WatershedUtils", "Context", "Plan",
     "WatershedError", "default_context", "load_library", "prelude",
 ]
+# `strips` (row-strip decomposition over several GPUs) imports torch; load it on demand:
+#   from rustronomy_watershed_b200 import strips

@@ -41,6 +41,11 @@ class WsHookCtx(C.Structure):
                 ("seeds", C.c_void_p), ("nseeds", C.c_size_t)]
 
 
+class WsStrip(C.Structure):
+    _fields_ = [("global_rows", C.c_size_t), ("row_offset", C.c_size_t), ("halo_top", C.c_uint8),
+                ("halo_bottom", C.c_uint8), ("colour_base", C.c_uint32)]
+
+
 HOOK_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(WsHookCtx))
 
 # name -> (restype, argtypes); every symbol include/ws_b200.h declares
@@ -83,6 +88,16 @@ SIGNATURES = {
     "ws_dev_free": (C.c_int, [_P, _P]),
     "ws_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "ws_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "ws_memcpy_d2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "ws_plan_strip_begin": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsStrip), _P, _P, C.c_size_t]),
+    "ws_plan_strip_export_times": (C.c_int, [_P, _P, _P]),
+    "ws_plan_strip_import_times": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int)]),
+    "ws_plan_strip_labels": (C.c_int, [_P]),
+    "ws_plan_strip_export_labels": (C.c_int, [_P, _P, _P]),
+    "ws_plan_strip_import_labels": (C.c_int, [_P, _P, _P, C.POINTER(C.c_size_t)]),
+    "ws_plan_strip_edges": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_uint32)]),
+    "ws_plan_union_edges": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint8]),
     "ws_plan_stats": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8)]),
     "ws_plan_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float * 4)]),
 }
@@ -180,6 +195,9 @@ class Context:
         a = np.ascontiguousarray(arr)
         self.check(self.lib.ws_memcpy_h2d(self.handle, d_ptr, a.ctypes.data, a.nbytes))
 
+    def d2d(self, d_dst: int, d_src: int, nbytes: int):
+        self.check(self.lib.ws_memcpy_d2d(self.handle, d_dst, d_src, nbytes))
+
     def d2h(self, d_ptr: int, shape, dtype) -> np.ndarray:
         out = np.empty(shape, dtype=dtype)
         self.check(self.lib.ws_memcpy_d2h(self.handle, out.ctypes.data, d_ptr, out.nbytes))
@@ -252,6 +270,42 @@ class Plan:
     @property
     def lake_counts_ptr(self) -> int:
         return int(self.lib.ws_plan_lake_counts(self.handle) or 0)
+
+    # -- row strips of one large field (ws_plan_strip_*) -----------------------------------
+    def strip_begin(self, kind: int, max_water_level: int, global_rows: int, row_offset: int, halo_top: bool,
+                    halo_bottom: bool, colour_base: int, d_img: int, d_seeds_rc: int, nseeds: int):
+        cfg = make_config(kind, max_water_level, False)
+        st = WsStrip(global_rows, row_offset, 1 if halo_top else 0, 1 if halo_bottom else 0, colour_base)
+        self.ctx.check(self.lib.ws_plan_strip_begin(self.handle, C.byref(cfg), C.byref(st), d_img, d_seeds_rc, nseeds))
+
+    def strip_export_times(self, d_top: int, d_bottom: int):
+        self.ctx.check(self.lib.ws_plan_strip_export_times(self.handle, d_top or None, d_bottom or None))
+
+    def strip_import_times(self, d_top: int, d_bottom: int) -> bool:
+        ch = C.c_int(0)
+        self.ctx.check(self.lib.ws_plan_strip_import_times(self.handle, d_top or None, d_bottom or None, C.byref(ch)))
+        return bool(ch.value)
+
+    def strip_labels(self):
+        self.ctx.check(self.lib.ws_plan_strip_labels(self.handle))
+
+    def strip_export_labels(self, d_top: int, d_bottom: int):
+        self.ctx.check(self.lib.ws_plan_strip_export_labels(self.handle, d_top or None, d_bottom or None))
+
+    def strip_import_labels(self, d_top: int, d_bottom: int) -> int:
+        n = C.c_size_t(0)
+        self.ctx.check(self.lib.ws_plan_strip_import_labels(self.handle, d_top or None, d_bottom or None, C.byref(n)))
+        return int(n.value)
+
+    def strip_edges(self):
+        """-> (device ptr of uint32 pairs, device ptr of level bytes, count, colours present)."""
+        ab, w, n, nd = _P(), _P(), C.c_size_t(0), C.c_uint32(0)
+        self.ctx.check(self.lib.ws_plan_strip_edges(self.handle, C.byref(ab), C.byref(w), C.byref(n), C.byref(nd)))
+        return int(ab.value or 0), int(w.value or 0), int(n.value), int(nd.value)
+
+    def union_edges(self, d_ab: int, d_w: int, n: int, ncolours: int, ndistinct: int, max_water_level: int):
+        self.ctx.check(self.lib.ws_plan_union_edges(self.handle, d_ab or None, d_w or None, n, ncolours, ndistinct,
+                                                    max_water_level))
 
     def snapshot(self, kind: int, i: int, level: int, d_out: int):
         self.ctx.check(self.lib.ws_plan_snapshot(self.handle, kind, i, level, d_out))

@@ -43,6 +43,16 @@ struct ImageDims {
   int n_img;      // slices in the batch
   int rows, cols; // per slice
   int tiles_x, tiles_y;
+  // Row-strip decomposition of one large field (n_img == 1): this plan holds rows
+  // [row_offset, row_offset + rows) of a field of global_rows rows; its first / last row is a halo
+  // copy of a neighbouring strip's row when halo_top / halo_bottom is set.  Plain plans: 0, rows, 0, 0.
+  int row_offset, global_rows, halo_top, halo_bottom;
+  __host__ __device__ bool is_halo_row(int r) const { return (halo_top && r == 0) || (halo_bottom && r == rows - 1); }
+  // window centre of the WHOLE field (lib.rs:220, 411-414), in local coordinates
+  __host__ __device__ bool is_centre(int r, int c) const {
+    const int gr = r + row_offset;
+    return gr >= 1 && gr <= global_rows - 2 && c >= 1 && c <= cols - 2;
+  }
   __host__ __device__ size_t px_per_img() const { return (size_t)rows * (size_t)cols; }
   __host__ __device__ size_t px_total() const { return px_per_img() * (size_t)n_img; }
   __host__ __device__ int tiles_per_img() const { return tiles_x * tiles_y; }

@@ -52,6 +52,11 @@ struct ws_plan {
   uint32_t* rep = nullptr;
   int rep_level = -1;
   uint32_t* T_dense = nullptr;       // lazily made dense copy of the arrival times (diagnostic accessor)
+  uint32_t* lvl_hist = nullptr;      // [n_img][256] pixels coloured at each level
+  uint32_t* d_strip_off = nullptr;   // [2] seed offsets {0, nseeds} of a strip run
+  uint32_t colour_base = 0;          // strips: colour of local seed i = colour_base + i + 1
+  uint2* union_edges = nullptr;      // ws_plan_union_edges: the gathered edges bucketed by level
+  size_t union_edges_cap = 0;
   uint32_t* chunk_counts = nullptr;  // minima scratch
   uint32_t* d_total = nullptr;
   uint32_t* h_ctrl = nullptr;        // pinned mirror of fb.ctrl + scalars
@@ -110,6 +115,9 @@ ImageDims make_dims(size_t n_img, size_t rows, size_t cols) {
   d.cols = (int)cols;
   d.tiles_x = (int)((cols + TILE_W - 1) / TILE_W);
   d.tiles_y = (int)((rows + TILE_H - 1) / TILE_H);
+  d.row_offset = 0;
+  d.global_rows = (int)rows;
+  d.halo_top = d.halo_bottom = 0;
   return d;
 }
 
@@ -271,6 +279,8 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->mb.level_hist, 257 * 4);
   alloc((void**)&p->mb.level_cursor, 256 * 4);
   alloc((void**)&p->mb.red_count, 16);
+  alloc((void**)&p->lvl_hist, n_img * 256 * 4);
+  alloc((void**)&p->d_strip_off, 16);
   alloc((void**)&p->mb.unions, n_img * 256 * 4);
   alloc((void**)&p->mb.ndistinct, n_img * 4);
   alloc((void**)&p->mb.counts, n_img * 256 * 4);
@@ -295,6 +305,9 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->fb.T);
   cudaFree(p->fb.pix);
   cudaFree(p->T_dense);
+  cudaFree(p->lvl_hist);
+  cudaFree(p->d_strip_off);
+  cudaFree(p->union_edges);
   cudaFree(p->fb.lab);
   cudaFree(p->fb.lvl);
   cudaFree(p->fb.lists);
@@ -376,7 +389,7 @@ static ws_status plan_merge(ws_plan* p) {
   WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
   WS_CUDA(ctx, launch_lake_counts(p->mb, p->d.n_img, lmax, s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
-  p->stats[4] += 7;
+  p->stats[4] += 8;
   p->merged = true;
   p->rep_level = -1;
   return WS_OK;
@@ -390,6 +403,9 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   if (nseeds_total >= 0x7fffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "more than 2^31 - 2 seeds");
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
+  p->d.row_offset = 0;  // a plain run: not a strip of a larger field
+  p->d.global_rows = p->d.rows;
+  p->d.halo_top = p->d.halo_bottom = 0;
   p->cfg = *cfg;
   p->seeds = d_seeds_rc;
   p->seed_off = d_seed_off;
@@ -402,7 +418,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
   WS_CUDA(ctx, cudaEventRecord(p->ev[0], s));
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_imgs, cfg->max_water_level, s));
-  WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, s));
+  WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, 0u, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[1], s));
   WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, ctx->flood_grid, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
@@ -458,6 +474,14 @@ extern "C" ws_status ws_memcpy_d2h(ws_ctx* ctx, void* h_dst, const void* d_src, 
   return WS_OK;
 }
 
+extern "C" ws_status ws_memcpy_d2d(ws_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+  if (!ctx || (bytes && (!d_dst || !d_src))) return WS_ERR_INVALID_ARG;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return WS_OK;
+}
+
 extern "C" const uint32_t* ws_plan_arrival_times(const ws_plan* cp) {
   ws_plan* p = const_cast<ws_plan*>(cp);
   if (!p) return nullptr;  // also after a failed run: the diagnostic is most useful then
@@ -506,6 +530,205 @@ extern "C" ws_status ws_plan_snapshot(ws_plan* p, ws_kind kind, size_t i, uint8_
   }
   WS_CUDA(ctx, launch_snapshot(p->fb.lab + i * n, p->fb.lvl + i * n, n, level, rep, base, d_out, ctx->stream));
   p->stats[4] += 1;
+  return WS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// row-strip decomposition of one field over several plans / GPUs
+// ---------------------------------------------------------------------------
+
+namespace {
+ws_status check_flood_errors(ws_plan* p) {
+  ws_ctx* ctx = p->ctx;
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl, p->fb.ctrl, FC_WORDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  p->stats[0] += p->h_ctrl[FC_SWEEPS];
+  p->stats[1] += p->h_ctrl[FC_ACTIVATIONS];
+  const uint32_t err = p->h_ctrl[FC_ERROR];
+  if (err & 1u) return fail(ctx, WS_ERR_SEED_OOB, "a seed lies outside the strip");
+  if (err & 2u) return fail(ctx, WS_ERR_HOP_OVERFLOW, ws_status_str(WS_ERR_HOP_OVERFLOW));
+  if (err & 4u) return fail(ctx, WS_ERR_INTERNAL, "flood did not reach a fixed point");
+  return WS_OK;
+}
+int first_owned(const ws_plan* p) { return p->d.halo_top ? 1 : 0; }
+int last_owned(const ws_plan* p) { return p->d.rows - 1 - (p->d.halo_bottom ? 1 : 0); }
+}  // namespace
+
+extern "C" ws_status ws_plan_strip_begin(ws_plan* p, const ws_config* cfg, const ws_strip* st, const uint8_t* d_img,
+                                         const uint32_t* d_seeds_rc, size_t nseeds) {
+  if (!p || !st || !d_img || (nseeds && !d_seeds_rc)) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  WS_TRY(check_cfg(ctx, cfg));
+  if (p->d.n_img != 1) return fail(ctx, WS_ERR_INVALID_ARG, "a strip plan holds one image");
+  if (st->row_offset + (size_t)p->d.rows > st->global_rows || (st->halo_top && st->row_offset == 0) ||
+      (size_t)p->d.rows < (size_t)(st->halo_top ? 1 : 0) + (st->halo_bottom ? 1 : 0) + 1)
+    return fail(ctx, WS_ERR_INVALID_ARG, "inconsistent strip geometry");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  p->d.row_offset = (int)st->row_offset;
+  p->d.global_rows = (int)st->global_rows;
+  p->d.halo_top = st->halo_top ? 1 : 0;
+  p->d.halo_bottom = st->halo_bottom ? 1 : 0;
+  p->colour_base = st->colour_base;
+  p->cfg = *cfg;
+  p->seeds = d_seeds_rc;
+  p->seed_off = p->d_strip_off;
+  p->nseeds = nseeds;
+  p->ran = false;
+  p->merged = false;
+  for (auto& v : p->stats) v = 0;
+  p->h_seed_off.assign(2, 0);
+  p->h_seed_off[1] = (uint32_t)nseeds;
+  p->h_ctrl[FC_WORDS + 2] = 0;
+  p->h_ctrl[FC_WORDS + 3] = (uint32_t)nseeds;
+  WS_CUDA(ctx, cudaMemcpyAsync(p->d_strip_off, p->h_ctrl + FC_WORDS + 2, 8, cudaMemcpyHostToDevice, s));
+  const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
+  WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_img, cfg->max_water_level, s));
+  WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, p->d_strip_off, (uint32_t)nseeds, st->colour_base, s));
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, ctx->flood_grid, s));
+  p->stats[4] += 3;
+  return check_flood_errors(p);
+}
+
+extern "C" ws_status ws_plan_strip_export_times(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom) {
+  if (!p) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, launch_strip_export_T(p->fb.T, p->d, d_top ? first_owned(p) : -1, d_bottom ? last_owned(p) : -1, d_top,
+                                     d_bottom, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller hands the rows to another stream / NCCL
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_strip_import_times(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom,
+                                            int* changed) {
+  if (!p || !changed) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  *changed = 0;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // fresh worklists; keep the error word
+  WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl, 0, sizeof(uint32_t) * FC_ERROR, s));
+  WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl + FC_STRIP_CHANGED, 0, sizeof(uint32_t), s));
+  WS_CUDA(ctx, cudaMemsetAsync(p->fb.flags, 0, sizeof(uint32_t) * (size_t)p->d.tiles_total(), s));
+  if (d_top && p->d.halo_top) WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, 0, 1, d_top, s));
+  if (d_bottom && p->d.halo_bottom)
+    WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, p->d.rows - 1, p->d.rows - 2, d_bottom, s));
+  const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, ctx->flood_grid, s));  // returns at once if nothing woke up
+  p->stats[4] += 3;
+  WS_TRY(check_flood_errors(p));
+  *changed = p->h_ctrl[FC_STRIP_CHANGED] ? 1 : 0;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_strip_labels(ws_plan* p) {
+  if (!p) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, launch_parent(p->fb, p->d, ctx->stream));
+  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, ctx->stream));
+  p->stats[4] += 2;
+  WS_TRY(check_flood_errors(p));
+  p->ran = true;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_strip_export_labels(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom) {
+  if (!p) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, launch_strip_export_lab(p->fb.lab, p->d, d_top ? first_owned(p) : -1, d_bottom ? last_owned(p) : -1,
+                                       d_top, d_bottom, ctx->stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_strip_import_labels(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom,
+                                                 size_t* pending) {
+  if (!p || !pending) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (d_top && p->d.halo_top) WS_CUDA(ctx, launch_strip_import_lab(p->fb.lab, p->d, 0, d_top, s));
+  if (d_bottom && p->d.halo_bottom) WS_CUDA(ctx, launch_strip_import_lab(p->fb.lab, p->d, p->d.rows - 1, d_bottom, s));
+  WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl + FC_JUMP_FLAG0, 0, sizeof(uint32_t) * 3, s));
+  WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl + FC_STRIP_PENDING, 0, sizeof(uint32_t), s));
+  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
+  WS_CUDA(ctx, launch_strip_count_pending(p->fb.lab, p->d, first_owned(p), last_owned(p), p->fb.ctrl, s));
+  p->stats[4] += 4;
+  WS_TRY(check_flood_errors(p));
+  *pending = p->h_ctrl[FC_STRIP_PENDING];
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_strip_edges(ws_plan* p, const void** d_ab, const void** d_w, size_t* n,
+                                         uint32_t* ndistinct) {
+  if (!p || !d_ab || !d_w || !n || !ndistinct) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  if (!p->ran) return fail(ctx, WS_ERR_INVALID_ARG, "labels are not resolved yet");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t cap = merge_reduce_capacity(p->d);
+  if (cap > p->edges_cap || !p->mb.edges) {
+    cudaFree(p->mb.edges); cudaFree(p->mb.red_ab); cudaFree(p->mb.red_w);
+    p->mb.edges = p->mb.red_ab = nullptr; p->mb.red_w = nullptr; p->edges_cap = 0;
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.red_ab, cap * sizeof(uint2)));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.red_w, cap));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.edges, cap * sizeof(uint2)));
+    p->edges_cap = cap;
+  }
+  // labels are GLOBAL colours here (colour_base + i + 1), so the colour id is label - 1: offsets {0, ...}
+  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, p->cfg.max_water_level, p->mb.red_ab,
+                                   p->mb.red_w, p->mb.red_count, s));
+  WS_CUDA(ctx, launch_count_present(p->fb.lab, p->d, p->seeds, (uint32_t)p->nseeds, p->colour_base, p->mb.ndistinct, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.ndistinct, 4, cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));
+  p->stats[4] += 2;
+  *d_ab = p->mb.red_ab;
+  *d_w = p->mb.red_w;
+  *n = p->h_ctrl[FC_WORDS];
+  *ndistinct = p->h_ctrl[FC_WORDS + 1];
+  p->stats[3] = *n;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_plan_union_edges(ws_plan* p, const void* d_ab, const void* d_w, size_t n, size_t ncolours,
+                                         uint32_t ndistinct, uint8_t max_water_level) {
+  if (!p || (n && (!d_ab || !d_w))) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  if (ncolours >= 0x7fffffffull || n >= 0xffffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "edge or colour count too large");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  if (ncolours > p->uf_cap || !p->mb.parent) {
+    cudaFree(p->mb.parent); cudaFree(p->mb.hook_to); cudaFree(p->mb.hook_lvl);
+    p->mb.parent = p->mb.hook_to = nullptr; p->mb.hook_lvl = nullptr; p->uf_cap = 0;
+    const size_t m = std::max<size_t>(ncolours, 1);
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.parent, m * 4));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_to, m * 4));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_lvl, m));
+    p->uf_cap = m;
+  }
+  if (n > p->union_edges_cap || !p->union_edges) {
+    cudaFree(p->union_edges);
+    p->union_edges = nullptr; p->union_edges_cap = 0;
+    WS_CUDA(ctx, cudaMalloc((void**)&p->union_edges, std::max<size_t>(n, 16) * sizeof(uint2)));
+    p->union_edges_cap = std::max<size_t>(n, 16);
+  }
+  p->h_ctrl[FC_WORDS + 2] = (uint32_t)n;
+  p->h_ctrl[FC_WORDS + 3] = ndistinct;
+  WS_CUDA(ctx, cudaMemcpyAsync(p->mb.red_count, p->h_ctrl + FC_WORDS + 2, 4, cudaMemcpyHostToDevice, s));
+  MergeBuffers m = p->mb;
+  m.edges = p->union_edges;
+  WS_CUDA(ctx, launch_red_sort((const uint2*)d_ab, (const uint8_t*)d_w, m.red_count, m.level_hist, m.level_cursor,
+                               m.edges, s));
+  WS_CUDA(ctx, launch_uf_reset(m, (uint32_t)ncolours, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(m.ndistinct, p->h_ctrl + FC_WORDS + 3, 4, cudaMemcpyHostToDevice, s));
+  WS_CUDA(ctx, launch_union_levels(m, p->d_strip_off, 1, max_water_level, ctx->union_grid, s));
+  WS_CUDA(ctx, launch_lake_counts(m, 1, max_water_level, s));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));
+  p->stats[4] += 7;
   return WS_OK;
 }
 
@@ -867,16 +1090,12 @@ extern "C" ws_status ws_transform_lake_counts(ws_ctx* ctx, const ws_config* cfg,
   cudaStream_t s = ctx->stream;
   const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
   std::vector<uint32_t> h_hist(256), h_counts(256);
-  // level histogram -> uncoloured pixels per level (d_total scratch is too small: reuse unions' sibling)
-  uint32_t* d_hist = nullptr;
-  WS_CUDA(ctx, cudaMalloc((void**)&d_hist, 256 * 4));
-  cudaError_t e = launch_level_hist(p->fb.lvl, p->d, d_hist, s);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h_hist.data(), d_hist, 256 * 4, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess && cfg->kind == WS_MERGING)
-    e = cudaMemcpyAsync(h_counts.data(), p->mb.counts, 256 * 4, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(d_hist);
-  if (e != cudaSuccess) return cuda_fail(ctx, e, "ws_transform_lake_counts");
+  // level histogram -> uncoloured pixels per level
+  WS_CUDA(ctx, launch_level_hist(p->fb.lvl, p->d, p->lvl_hist, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(h_hist.data(), p->lvl_hist, 256 * 4, cudaMemcpyDeviceToHost, s));
+  if (cfg->kind == WS_MERGING)
+    WS_CUDA(ctx, cudaMemcpyAsync(h_counts.data(), p->mb.counts, 256 * 4, cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));
   p->stats[4] += 1;
   if (cfg->kind == WS_SEGMENTING) {
     // no merges: every colour present on the canvas is a lake at every level

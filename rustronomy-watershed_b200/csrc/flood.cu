@@ -131,7 +131,8 @@ __device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t ntiles
 // duplicate overwrites an earlier one (sequential loop) == the largest index wins.
 __global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDims d,
                                                         const uint32_t* __restrict__ seeds_rc,
-                                                        const uint32_t* __restrict__ seed_off, uint32_t nseeds) {
+                                                        const uint32_t* __restrict__ seed_off, uint32_t nseeds,
+                                                        uint32_t colour_base) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nseeds) return;
   int lo = 0, hi = d.n_img;  // slice of seed i: last b with seed_off[b] <= i
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDim
   }
   st_cg(&b.T[(size_t)img * d.t_plane() + d.t_index((int)r, (int)c)], 0u);
   atomicMax(&b.lab[(size_t)img * d.px_per_img() + (size_t)r * d.cols + c],
-            LAB_RESOLVED | (i - __ldg(seed_off + img) + 1u));
+            LAB_RESOLVED | (colour_base + i - __ldg(seed_off + img) + 1u));
   const uint32_t ntiles = (uint32_t)d.tiles_total();
   const int ty = r / TILE_H, tx = c / TILE_W;
   const uint32_t tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
@@ -159,9 +160,9 @@ __global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDim
 }
 
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
-                             uint32_t nseeds, cudaStream_t s) {
+                             uint32_t nseeds, uint32_t colour_base, cudaStream_t s) {
   if (nseeds == 0) return cudaSuccess;
-  seed_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds);
+  seed_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds, colour_base);
   return cudaGetLastError();
 }
 
@@ -526,6 +527,12 @@ __global__ void __launch_bounds__(256) parent_kernel(FloodBuffers b, ImageDims d
     b.lab[p] = LAB_RESOLVED;  // UNCOLOURED
     return;
   }
+  if (d.is_halo_row(r)) {
+    // a neighbouring strip owns this pixel: its label arrives by exchange; until then the word
+    // points at itself ("pending"), which pointer jumping leaves alone
+    b.lab[p] = (uint32_t)p;
+    return;
+  }
   if (t == 0u) return;  // seed: coloured by seed_init
   // A coloured non-seed pixel is interior, so all four neighbours exist.  The coloured
   // neighbours the reference sees when it colours p are exactly those with T(q) < T(p);
@@ -546,6 +553,91 @@ __global__ void __launch_bounds__(256) parent_kernel(FloodBuffers b, ImageDims d
 cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s) {
   dim3 grid((d.cols + 255) / 256, d.rows, d.n_img);
   parent_kernel<<<grid, 256, 0, s>>>(b, d);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// row-strip decomposition: boundary rows of arrival times and of labels
+// ---------------------------------------------------------------------------
+
+// rows `ra` / `rb` of the padded arrival times -> dense rows (negative row = skip)
+__global__ void __launch_bounds__(256) strip_export_T_kernel(const uint32_t* __restrict__ T, ImageDims d, int ra,
+                                                             int rb, uint32_t* __restrict__ out_a,
+                                                             uint32_t* __restrict__ out_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.cols) return;
+  if (ra >= 0) out_a[c] = ld_cg(T + d.t_index(ra, c));
+  if (rb >= 0) out_b[c] = ld_cg(T + d.t_index(rb, c));
+}
+
+// min-merge a neighbour's row into halo row `row`; where it got lower, wake the tile that holds the
+// adjacent owned row `nb_row`
+__global__ void __launch_bounds__(256) strip_import_T_kernel(FloodBuffers b, ImageDims d, int row, int nb_row,
+                                                             const uint32_t* __restrict__ in) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.cols) return;
+  const uint32_t v = in[c];
+  uint32_t* t = b.T + d.t_index(row, c);
+  if (v < ld_cg(t)) {
+    st_cg(t, v);
+    atomicOr(&b.ctrl[FC_STRIP_CHANGED], 1u);
+    push_tile(b, (uint32_t)d.tiles_total(), 0, (uint32_t)((nb_row / TILE_H) * d.tiles_x + c / TILE_W));
+  }
+}
+
+__global__ void __launch_bounds__(256) strip_export_lab_kernel(const uint32_t* __restrict__ lab, ImageDims d, int ra,
+                                                               int rb, uint32_t* __restrict__ out_a,
+                                                               uint32_t* __restrict__ out_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.cols) return;
+  if (ra >= 0) out_a[c] = ld_cg(lab + (size_t)ra * d.cols + c);
+  if (rb >= 0) out_b[c] = ld_cg(lab + (size_t)rb * d.cols + c);
+}
+
+// resolved labels of the neighbour's boundary row replace the pending words of halo row `row`
+__global__ void __launch_bounds__(256) strip_import_lab_kernel(uint32_t* __restrict__ lab, ImageDims d, int row,
+                                                               const uint32_t* __restrict__ in) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d.cols) return;
+  const uint32_t v = in[c];
+  uint32_t* l = lab + (size_t)row * d.cols + c;
+  if ((v & LAB_RESOLVED) && !(ld_cg(l) & LAB_RESOLVED)) st_cg(l, v);
+}
+
+// pixels of the owned rows [r0, r1] whose label is still a pointer
+__global__ void __launch_bounds__(256) strip_count_pending_kernel(const uint32_t* __restrict__ lab, ImageDims d,
+                                                                  int r0, int r1, uint32_t* __restrict__ ctrl) {
+  const size_t lo = (size_t)r0 * d.cols, hi = (size_t)(r1 + 1) * d.cols;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  int n = 0;
+  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride)
+    n += !(ld_cg(lab + i) & LAB_RESOLVED);
+  n = __syncthreads_count(n);  // number of THREADS with pending pixels is enough for a zero test...
+  if (threadIdx.x == 0 && n) atomicAdd(&ctrl[FC_STRIP_PENDING], (uint32_t)n);
+}
+
+cudaError_t launch_strip_export_T(const uint32_t* T, ImageDims d, int ra, int rb, uint32_t* out_a, uint32_t* out_b,
+                                  cudaStream_t s) {
+  strip_export_T_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(T, d, ra, rb, out_a, out_b);
+  return cudaGetLastError();
+}
+cudaError_t launch_strip_import_T(FloodBuffers b, ImageDims d, int row, int nb_row, const uint32_t* in,
+                                  cudaStream_t s) {
+  strip_import_T_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(b, d, row, nb_row, in);
+  return cudaGetLastError();
+}
+cudaError_t launch_strip_export_lab(const uint32_t* lab, ImageDims d, int ra, int rb, uint32_t* out_a,
+                                    uint32_t* out_b, cudaStream_t s) {
+  strip_export_lab_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(lab, d, ra, rb, out_a, out_b);
+  return cudaGetLastError();
+}
+cudaError_t launch_strip_import_lab(uint32_t* lab, ImageDims d, int row, const uint32_t* in, cudaStream_t s) {
+  strip_import_lab_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(lab, d, row, in);
+  return cudaGetLastError();
+}
+cudaError_t launch_strip_count_pending(const uint32_t* lab, ImageDims d, int r0, int r1, uint32_t* ctrl,
+                                       cudaStream_t s) {
+  strip_count_pending_kernel<<<148 * 4, 256, 0, s>>>(lab, d, r0, r1, ctrl);
   return cudaGetLastError();
 }
 

@@ -196,8 +196,10 @@ __global__ void __launch_bounds__(256) jump_kernel(uint32_t* __restrict__ lab, s
       const uint32_t v = ld_cg(lab + i);
       if (!(v & LAB_RESOLVED)) {
         const uint32_t w = ld_cg(lab + v);
-        st_cg(lab + i, w);
-        if (!(w & LAB_RESOLVED)) pending = 1;
+        if (w != v) {  // w == v: the chain ends at a pending halo pixel of a strip (points at itself)
+          st_cg(lab + i, w);
+          if (!(w & LAB_RESOLVED)) pending = 1;
+        }
       }
     }
     if (__syncthreads_or(pending) && threadIdx.x == 0) st_cg(&ctrl[FC_JUMP_FLAG0 + cur], 1u);
@@ -260,6 +262,43 @@ __global__ void __launch_bounds__(256) uf_init_kernel(MergeBuffers m, const uint
   }
 }
 
+// strips: union-find over GLOBAL colours, reset only (the number of colours present comes from the host)
+__global__ void __launch_bounds__(256) uf_reset_kernel(MergeBuffers m, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  m.parent[i] = i;
+  m.hook_to[i] = i;
+  m.hook_lvl[i] = 255;
+}
+cudaError_t launch_uf_reset(MergeBuffers m, uint32_t n, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(m.unions, 0, sizeof(uint32_t) * 256, s);
+  if (e != cudaSuccess || n == 0) return e;
+  uf_reset_kernel<<<(n + 255) / 256, 256, 0, s>>>(m, n);
+  return cudaGetLastError();
+}
+
+// strips: seeds of this strip whose pixel still carries their colour (not overwritten by a later duplicate)
+__global__ void __launch_bounds__(256) count_present_kernel(const uint32_t* __restrict__ lab, ImageDims d,
+                                                            const uint32_t* __restrict__ seeds_rc, uint32_t nseeds,
+                                                            uint32_t colour_base, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool present = false;
+  if (i < nseeds) {
+    const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
+    if (r < (uint32_t)d.rows && c < (uint32_t)d.cols)
+      present = (lab[(size_t)r * d.cols + c] & LAB_MASK) == colour_base + i + 1u;
+  }
+  const int n = __syncthreads_count(present);
+  if (threadIdx.x == 0 && n) atomicAdd(out, (uint32_t)n);
+}
+cudaError_t launch_count_present(const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc, uint32_t nseeds,
+                                 uint32_t colour_base, uint32_t* out, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess || nseeds == 0) return e;
+  count_present_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(lab, d, seeds_rc, nseeds, colour_base, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,
                            const uint32_t* seed_off, uint32_t nseeds, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(m.unions, 0, sizeof(uint32_t) * 256 * (size_t)d.n_img, s);
@@ -269,6 +308,7 @@ cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, con
   uf_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(m, lab, d, seeds_rc, seed_off, nseeds);
   return cudaGetLastError();
 }
+
 
 __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
   uint32_t p = ld_cg(parent + x);
@@ -281,9 +321,47 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
   return x;
 }
 
+constexpr uint32_t UNION_SMALL_LIMIT = 1u << 18;  // edge lists up to this size go through ONE CTA
+
+// Small edge lists (e.g. a 512x512 field: ~4e4 forest edges): one CTA, a CTA barrier per level
+// (~0.1 us) instead of a grid barrier over a thousand CTAs (~5 us) -- 255 levels make the difference.
+__global__ void __launch_bounds__(1024) union_levels_small_kernel(MergeBuffers m,
+                                                                  const uint32_t* __restrict__ seed_off, int n_img,
+                                                                  uint32_t lmax) {
+  if (m.level_hist[256] > UNION_SMALL_LIMIT) return;  // the cooperative kernel takes it
+  for (uint32_t l = 0; l <= lmax; ++l) {
+    const uint32_t lo = m.level_hist[l], hi = m.level_hist[l + 1];
+    if (lo == hi) continue;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const uint2 e = m.edges[i];
+      uint32_t a = e.x, b = e.y;
+      for (;;) {
+        a = uf_find(m.parent, a);
+        b = uf_find(m.parent, b);
+        if (a == b) break;
+        if (a < b) { const uint32_t t = a; a = b; b = t; }
+        if (atomicCAS(m.parent + a, a, b) == a) {
+          m.hook_to[a] = b;
+          m.hook_lvl[a] = (uint8_t)l;
+          int s0 = 0, s1 = n_img;
+          while (s1 - s0 > 1) {
+            const int mid = (s0 + s1) >> 1;
+            if (__ldg(seed_off + mid) <= a) s0 = mid; else s1 = mid;
+          }
+          atomicAdd(&m.unions[(size_t)s0 * 256 + l], 1u);
+          break;
+        }
+      }
+    }
+    __threadfence();
+    __syncthreads();
+  }
+}
+
 // All levels in one persistent cooperative kernel; a grid barrier separates the levels.
 __global__ void __launch_bounds__(256) union_levels_kernel(MergeBuffers m, const uint32_t* __restrict__ seed_off,
                                                            int n_img, uint32_t lmax) {
+  if (m.level_hist[256] <= UNION_SMALL_LIMIT) return;  // handled by union_levels_small_kernel
   cg::grid_group grid = cg::this_grid();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   __shared__ uint32_t s_ok;  // successes of this CTA at the current level (single-slice runs)
@@ -327,6 +405,9 @@ int union_max_grid(int device) { return coop_max_grid((const void*)union_levels_
 
 cudaError_t launch_union_levels(MergeBuffers m, const uint32_t* seed_off, int n_img, uint32_t lmax, int grid,
                                 cudaStream_t s) {
+  union_levels_small_kernel<<<1, 1024, 0, s>>>(m, seed_off, n_img, lmax);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
   void* args[] = {&m, &seed_off, &n_img, &lmax};
   return cudaLaunchCooperativeKernel((const void*)union_levels_kernel, dim3(grid), dim3(256), args, 0, s);
 }

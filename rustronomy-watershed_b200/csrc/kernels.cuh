@@ -15,6 +15,8 @@ enum FloodCtrl {
   FC_ERROR = 8,    // bit 0: seed out of bounds, bit 1: hop overflow, bit 2: orphan pixel
   FC_JUMP_FLAG0 = 9,  // [9..11] rotating "still unresolved" flags of the pointer jumping
   FC_JUMP_ROUNDS = 12,
+  FC_STRIP_CHANGED = 13,  // a halo row of arrival times got lower on import
+  FC_STRIP_PENDING = 14,  // owned pixels whose label is still a pointer
   FC_WORDS = 16
 };
 
@@ -46,7 +48,17 @@ cudaError_t launch_minima_write(const uint8_t* img, ImageDims d, const uint32_t*
 // --- flood (find_flooded_px + write-back over all levels, lib.rs:196-257, 1379-1438) ---
 cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, cudaStream_t s);
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
-                             uint32_t nseeds, cudaStream_t s);
+                             uint32_t nseeds, uint32_t colour_base, cudaStream_t s);
+// row-strip decomposition: boundary rows of arrival times / labels (flood.cu)
+cudaError_t launch_strip_export_T(const uint32_t* T, ImageDims d, int ra, int rb, uint32_t* out_a, uint32_t* out_b,
+                                  cudaStream_t s);
+cudaError_t launch_strip_import_T(FloodBuffers b, ImageDims d, int row, int nb_row, const uint32_t* in,
+                                  cudaStream_t s);
+cudaError_t launch_strip_export_lab(const uint32_t* lab, ImageDims d, int ra, int rb, uint32_t* out_a,
+                                    uint32_t* out_b, cudaStream_t s);
+cudaError_t launch_strip_import_lab(uint32_t* lab, ImageDims d, int row, const uint32_t* in, cudaStream_t s);
+cudaError_t launch_strip_count_pending(const uint32_t* lab, ImageDims d, int r0, int r1, uint32_t* ctrl,
+                                       cudaStream_t s);
 cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseeds, size_t rows, size_t cols,
                                  cudaStream_t s);
 cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int grid, cudaStream_t s);
@@ -80,6 +92,9 @@ cudaError_t launch_red_sort(const uint2* red_ab, const uint8_t* red_w, const uin
                             uint32_t* level_hist, uint32_t* level_cursor, uint2* edges, cudaStream_t s);
 cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,
                            const uint32_t* seed_off, uint32_t nseeds, cudaStream_t s);
+cudaError_t launch_uf_reset(MergeBuffers m, uint32_t n, cudaStream_t s);
+cudaError_t launch_count_present(const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc, uint32_t nseeds,
+                                 uint32_t colour_base, uint32_t* out, cudaStream_t s);
 cudaError_t launch_union_levels(MergeBuffers m, const uint32_t* seed_off, int n_img, uint32_t lmax, int grid,
                                 cudaStream_t s);
 cudaError_t launch_lake_counts(MergeBuffers m, int n_img, uint32_t lmax, cudaStream_t s);

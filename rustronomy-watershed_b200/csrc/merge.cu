@@ -101,18 +101,18 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     const int gr = r0 + r, gc = c0 + lc;
     const uint32_t a = sm.lab[n];
     uint32_t wr = 0xFFu, wd = 0xFFu;
-    if (a != 0u) {
-      const bool pin = gr >= 1 && gr <= d.rows - 2 && gc >= 1 && gc <= d.cols - 2;
+    // An edge belongs to the strip that owns its upper / left pixel; a halo row's own edges are the
+    // neighbouring strip's.  Plain plans own every row.
+    if (a != 0u && gr < d.rows && !(d.halo_top && gr == 0) && !(d.halo_bottom && gr == d.rows - 1)) {
+      const bool pin = d.is_centre(gr, gc);
       const uint32_t br = sm.lab[n + 1], bd = sm.lab[n + MR_NW];
       if (br != 0u) {
         if (br == a) sm_union(sm.parent, n, n + 1);
-        else if (pin || (gr >= 1 && gr <= d.rows - 2 && gc + 1 <= d.cols - 2))
-          wr = max((uint32_t)sm.lvl[n], (uint32_t)sm.lvl[n + 1]);
+        else if (pin || d.is_centre(gr, gc + 1)) wr = max((uint32_t)sm.lvl[n], (uint32_t)sm.lvl[n + 1]);
       }
       if (bd != 0u) {
         if (bd == a) sm_union(sm.parent, n, n + MR_NW);
-        else if (pin || (gc >= 1 && gc <= d.cols - 2 && gr + 1 <= d.rows - 2))
-          wd = max((uint32_t)sm.lvl[n], (uint32_t)sm.lvl[n + MR_NW]);
+        else if (pin || d.is_centre(gr + 1, gc)) wd = max((uint32_t)sm.lvl[n], (uint32_t)sm.lvl[n + MR_NW]);
       }
     }
     ew[i] = wr | (wd << 8);
