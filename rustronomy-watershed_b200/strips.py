@@ -196,6 +196,7 @@ class CudaStrip:
         return top, bot
 
     def import_times(self, top, bottom) -> bool:
+        torch.cuda.current_stream(self.dev).synchronize()      # rows received / cloned on torch's stream
         return self.plan.strip_import_times(top.data_ptr() if top is not None else 0,
                                             bottom.data_ptr() if bottom is not None else 0)
 
@@ -210,6 +211,7 @@ class CudaStrip:
         return top, bot
 
     def import_labels(self, top, bottom) -> int:
+        torch.cuda.current_stream(self.dev).synchronize()
         return self.plan.strip_import_labels(top.data_ptr() if top is not None else 0,
                                              bottom.data_ptr() if bottom is not None else 0)
 
@@ -224,6 +226,8 @@ class CudaStrip:
 
     def union(self, ab, w, ncolours: int, ndistinct: int, lmax: int) -> np.ndarray:
         n = int(ab.shape[0]) if ab is not None else 0
+        # ab / w were produced on torch's stream (all-gather, cat); the library runs on its own stream
+        torch.cuda.current_stream(self.dev).synchronize()
         self.plan.union_edges(ab.data_ptr() if n else 0, w.data_ptr() if n else 0, n, ncolours, ndistinct, lmax)
         return self.ctx.d2h(self.plan.lake_counts_ptr, (256,), np.uint32)
 
