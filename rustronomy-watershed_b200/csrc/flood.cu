@@ -89,23 +89,39 @@ __global__ void __launch_bounds__(256) fill_state_kernel(FloodBuffers b, ImageDi
                                                          uint32_t lmax) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nt = d.t_plane() * d.n_img;
-  for (size_t i = tid; i < nt; i += stride) __stcg(b.T + i, T_INF);
-  const size_t nl = d.px_total();
-  for (size_t i = tid; i < nl; i += stride) __stcg(b.lab + i, 0u);
+  // arrival times: the padded plane is a multiple of 8 words
+  const size_t nt4 = d.t_plane() * d.n_img / 4;
+  const uint4 inf4 = make_uint4(T_INF, T_INF, T_INF, T_INF);
+  uint4* T4 = reinterpret_cast<uint4*>(b.T);
+  for (size_t i = tid; i < nt4; i += stride) __stcg(T4 + i, inf4);
+  // labels
+  const size_t nl = d.px_total(), nl4 = nl / 4;
+  uint4* L4 = reinterpret_cast<uint4*>(b.lab);
+  for (size_t i = tid; i < nl4; i += stride) __stcg(L4 + i, make_uint4(0u, 0u, 0u, 0u));
+  for (size_t i = nl4 * 4 + tid; i < nl; i += stride) b.lab[i] = 0u;
+  // image bytes, four per thread (the padded rows are multiples of 64 bytes)
   const size_t pp = d.pix_plane();
   const int ppitch = d.pix_pitch();
-  const size_t np = pp * d.n_img;
-  for (size_t i = tid; i < np; i += stride) {
-    const int im = (int)(i / pp);
-    const size_t rem = i - (size_t)im * pp;
-    const int r = (int)(rem / ppitch), c = (int)(rem - (size_t)r * ppitch);
-    uint32_t v = 255u;
-    if (r >= 1 && r <= d.rows - 2 && c >= 1 && c <= d.cols - 2) {
-      v = __ldg(img + (size_t)im * d.px_per_img() + (size_t)r * d.cols + c);
-      if (v > lmax) v = 255u;
+  const size_t np4 = pp * d.n_img / 4;
+  uchar4* P4 = reinterpret_cast<uchar4*>(b.pix);
+  for (size_t i = tid; i < np4; i += stride) {
+    const size_t e = i * 4;
+    const int im = (int)(e / pp);
+    const size_t rem = e - (size_t)im * pp;
+    const int r = (int)(rem / ppitch), c0 = (int)(rem - (size_t)r * ppitch);
+    uint32_t v[4] = {255u, 255u, 255u, 255u};
+    if (r >= 1 && r <= d.rows - 2) {
+      const uint8_t* row = img + (size_t)im * d.px_per_img() + (size_t)r * d.cols;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c0 + k;
+        if (c >= 1 && c <= d.cols - 2) {
+          const uint32_t x = __ldg(row + c);
+          v[k] = x > lmax ? 255u : x;
+        }
+      }
     }
-    b.pix[i] = (uint8_t)v;
+    P4[i] = make_uchar4((unsigned char)v[0], (unsigned char)v[1], (unsigned char)v[2], (unsigned char)v[3]);
   }
 }
 
@@ -120,6 +136,7 @@ cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, u
 
 __device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t ntiles, int list, uint32_t tile) {
   const uint32_t bit = 1u << list;
+  if (ld_cg(&b.flags[tile]) & bit) return;  // already queued (the common case when seeds are dense)
   const uint32_t old = atomicOr(&b.flags[tile], bit);
   if (!(old & bit)) {
     const uint32_t pos = atomicAdd(&b.ctrl[FC_COUNT0 + list], 1u);
