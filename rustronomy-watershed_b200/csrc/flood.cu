@@ -166,14 +166,19 @@ __global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDim
   st_cg(&b.T[(size_t)img * d.t_plane() + d.t_index((int)r, (int)c)], 0u);
   atomicMax(&b.lab[(size_t)img * d.px_per_img() + (size_t)r * d.cols + c],
             LAB_RESOLVED | (colour_base + i - __ldg(seed_off + img) + 1u));
+  // Red-black order over the tiles: the first sweep takes the even tiles (tx + ty even), the second the
+  // odd ones -- which then already see their neighbours' results, a Gauss-Seidel step at tile level
+  // that saves re-activations.  A tile's 4-neighbours have the other parity, so later sweeps alternate
+  // by themselves; only the seeding has to split the lists.
   const uint32_t ntiles = (uint32_t)d.tiles_total();
   const int ty = r / TILE_H, tx = c / TILE_W;
   const uint32_t tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
-  push_tile(b, ntiles, 0, tile);
-  if (r % TILE_H == 0 && ty > 0) push_tile(b, ntiles, 0, tile - d.tiles_x);
-  if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile(b, ntiles, 0, tile + d.tiles_x);
-  if (c % TILE_W == 0 && tx > 0) push_tile(b, ntiles, 0, tile - 1);
-  if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile(b, ntiles, 0, tile + 1);
+  const int par = (tx + ty) & 1;
+  push_tile(b, ntiles, par, tile);
+  if (r % TILE_H == 0 && ty > 0) push_tile(b, ntiles, par ^ 1, tile - d.tiles_x);
+  if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile(b, ntiles, par ^ 1, tile + d.tiles_x);
+  if (c % TILE_W == 0 && tx > 0) push_tile(b, ntiles, par ^ 1, tile - 1);
+  if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile(b, ntiles, par ^ 1, tile + 1);
 }
 
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
@@ -376,9 +381,11 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(FloodArgs a) {
 
   uint32_t slot = 0;  // ring slots used so far (same sequence on both sides); stage = slot & 1
   int cur = 0;
-  for (;;) {
+  for (uint32_t sweep = 0;; ++sweep) {
     const uint32_t n = ld_cg(&a.b.ctrl[FC_COUNT0 + cur]);
-    if (n == 0) break;
+    // an empty list ends the flood -- except the very first one (even tiles), after which the odd
+    // tiles seeded into list 1 still have to run
+    if (n == 0 && (sweep > 0 || ld_cg(&a.b.ctrl[FC_COUNT0 + 1]) == 0)) break;
     const int nxt = (cur + 1) % 3, old = (cur + 2) % 3;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       st_cg(&a.b.ctrl[FC_COUNT0 + old], 0u);
