@@ -344,16 +344,21 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
   uint32_t* Tg = a.b.T + (size_t)img * d.t_plane() +
                  d.t_index(ty * TILE_H + cgp * ROWS_PER_THREAD, tx * TILE_W + cl);
   const int tp = d.t_pitch();
+  // A neighbour tile re-runs only if a changed edge pixel can still lower the pixel facing it:
+  // T(edge) + 1 < T(facing pixel), the latter as staged in our halo (never newer than the truth, so the
+  // test never drops a needed wake-up).  Without it every tile woke all four neighbours, including the
+  // one its values came from, and most activations were such echoes.
   uint32_t e = 0;
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     const uint32_t v = colp[i * SM_W];
     if (v != st.T[(cgp * ROWS_PER_THREAD + i + 1) * STG_W + cl + T_PAD_L]) {
       st_cg(Tg + (size_t)i * tp, v);
-      if (cl == 0) e |= EDGE_LEFT;
-      if (cl == TILE_W - 1) e |= EDGE_RIGHT;
-      if (cgp == 0 && i == 0) e |= EDGE_UP;
-      if (cgp == TILE_H / ROWS_PER_THREAD - 1 && i == ROWS_PER_THREAD - 1) e |= EDGE_DOWN;
+      if (cl == 0 && v + 1u < colp[i * SM_W - 1]) e |= EDGE_LEFT;
+      if (cl == TILE_W - 1 && v + 1u < colp[i * SM_W + 1]) e |= EDGE_RIGHT;
+      if (cgp == 0 && i == 0 && v + 1u < colp[-SM_W]) e |= EDGE_UP;
+      if (cgp == TILE_H / ROWS_PER_THREAD - 1 && i == ROWS_PER_THREAD - 1 && v + 1u < colp[ROWS_PER_THREAD * SM_W])
+        e |= EDGE_DOWN;
     }
   }
   if (e) atomicOr(&sm.edge[s], e);
