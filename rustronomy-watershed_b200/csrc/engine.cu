@@ -437,6 +437,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   if (p->merged) p->stats[3] = p->h_ctrl[FC_WORDS + 1];
   p->stats[1] = p->h_ctrl[FC_ACTIVATIONS];
   p->stats[2] = p->h_ctrl[FC_JUMP_ROUNDS];
+  p->stats[5] = p->h_ctrl[FC_PHASES];
   const uint32_t err = p->h_ctrl[FC_ERROR];
   if (err & 1u) return fail(ctx, WS_ERR_SEED_OOB, "a seed lies outside the image");
   if (err & 2u) return fail(ctx, WS_ERR_HOP_OVERFLOW, ws_status_str(WS_ERR_HOP_OVERFLOW));

@@ -275,7 +275,9 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
   }
 
   bool ovf = false;
+  uint32_t nphase = 0;
   for (;;) {
+    nphase += 2;
     {  // ---- column phase: T(p) = max(A(p), 1 + min over the 4 neighbours) down then up ----
       uint32_t t[ROWS_PER_THREAD], m[ROWS_PER_THREAD];
       const uint32_t up = colp[-SM_W], dn = colp[ROWS_PER_THREAD * SM_W];
@@ -362,6 +364,7 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
     }
   }
   if (e) atomicOr(&sm.edge[s], e);
+  if (tid == 0) atomicAdd(&a.b.ctrl[FC_PHASES], nphase);
   if (a.check_overflow && ovf) atomicOr(&a.b.ctrl[FC_ERROR], 2u);
 }
 

@@ -17,6 +17,7 @@ enum FloodCtrl {
   FC_JUMP_ROUNDS = 12,
   FC_STRIP_CHANGED = 13,  // a halo row of arrival times got lower on import
   FC_STRIP_PENDING = 14,  // owned pixels whose label is still a pointer
+  FC_PHASES = 15,         // in-tile phases run (diagnostic)
   FC_WORDS = 16
 };
 
