@@ -266,7 +266,7 @@ def main():
         sst = plan.stats()
         extra = {"workload": f"{S}x{S} u8 Gaussian-smoothed field (sigma 16), segmenting + merging", "seeds": ns,
                  "ms_per_step": sms, "value": px_levels_step / (sms * 1e-3) / 1e6, "unit": UNIT,
-                 "flood_ms": float(np.mean(fl)), "flood_sweeps": sst["flood_sweeps"],
+                 "flood_ms": float(np.mean(fl)), "stale_entries": sst["stale_entries"],
                  "tile_activations": sst["tile_activations"]}
         # back to the headline field for everything below
         plan.find_local_minima(d_img.data_ptr(), d_seeds.data_ptr(), nseeds, d_off.data_ptr())

@@ -240,7 +240,7 @@ const uint32_t *ws_plan_arrival_times(const ws_plan *plan);
  * (rows*cols).  Merging snapshots need the run to have been WS_MERGING.       */
 ws_status ws_plan_snapshot(ws_plan *plan, ws_kind kind, size_t i, uint8_t level,
                            uint64_t *d_out);
-/* Counters of the last run: [0] flood sweeps, [1] tile activations,
+/* Counters of the last run: [0] stale worklist entries dropped, [1] tile activations,
  * [2] pointer-jumping rounds, [3] merge edges, [4] kernels launched,
  * [5] in-tile iteration phases of the flood.                                  */
 ws_status ws_plan_stats(ws_plan *plan, uint64_t out[8]);

@@ -318,5 +318,5 @@ class Plan:
     def stats(self) -> dict:
         arr = (C.c_uint64 * 8)()
         self.ctx.check(self.lib.ws_plan_stats(self.handle, C.byref(arr)))
-        return {"flood_sweeps": arr[0], "tile_activations": arr[1], "jump_rounds": arr[2],
+        return {"stale_entries": arr[0], "tile_activations": arr[1], "jump_rounds": arr[2],
                 "merge_edges": arr[3], "kernel_launches": arr[4], "flood_phases": arr[5]}

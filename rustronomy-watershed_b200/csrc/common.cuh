@@ -68,6 +68,14 @@ struct ImageDims {
 };
 
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { return __ldcg(p); }
+// Polling load: relaxed, GPU scope, with a memory clobber.  __ldcg is an `asm volatile` WITHOUT the
+// clobber, and nvcc hoists it out of a spin loop as loop-invariant (seen in SASS: one LDG followed by a
+// counting loop that never reloads).  Everything that waits for another CTA's write uses this one.
+__device__ __forceinline__ uint32_t ld_poll(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_cg(uint32_t* p, uint32_t v) { __stcg(p, v); }
 
 __device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }

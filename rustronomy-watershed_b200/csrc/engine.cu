@@ -55,6 +55,7 @@ struct ws_plan {
   uint32_t* lvl_hist = nullptr;      // [n_img][256] pixels coloured at each level
   uint32_t* d_strip_off = nullptr;   // [2] seed offsets {0, nseeds} of a strip run
   uint32_t colour_base = 0;          // strips: colour of local seed i = colour_base + i + 1
+  int bucket_shift = 2;              // priority granularity of the flood's worklist in the last run
   uint2* union_edges = nullptr;      // ws_plan_union_edges: the gathered edges bucketed by level
   size_t union_edges_cap = 0;
   uint32_t* chunk_counts = nullptr;  // minima scratch
@@ -273,8 +274,9 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->fb.pix, p->d.pix_plane() * n_img);
   alloc((void**)&p->fb.lab, npx * 4);
   alloc((void**)&p->fb.lvl, npx);
-  alloc((void**)&p->fb.lists, ntiles * 3 * 4);
-  alloc((void**)&p->fb.flags, ntiles * 4);
+  p->fb.qcap = (uint32_t)ntiles + FLOOD_QSLACK;
+  alloc((void**)&p->fb.qslots, (size_t)FLOOD_BUCKETS * p->fb.qcap * 4);
+  alloc((void**)&p->fb.qmask, ntiles * 8);
   alloc((void**)&p->fb.ctrl, FC_WORDS * 4);
   alloc((void**)&p->mb.level_hist, 257 * 4);
   alloc((void**)&p->mb.level_cursor, 256 * 4);
@@ -310,8 +312,8 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->union_edges);
   cudaFree(p->fb.lab);
   cudaFree(p->fb.lvl);
-  cudaFree(p->fb.lists);
-  cudaFree(p->fb.flags);
+  cudaFree(p->fb.qslots);
+  cudaFree(p->fb.qmask);
   cudaFree(p->fb.ctrl);
   cudaFree(p->mb.level_hist);
   cudaFree(p->mb.level_cursor);
@@ -420,7 +422,8 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_imgs, cfg->max_water_level, s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, 0u, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[1], s));
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, ctx->flood_grid, s));
+  p->bucket_shift = flood_bucket_shift(nseeds_total, p->d);
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
   WS_CUDA(ctx, launch_parent(p->fb, p->d, s));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
@@ -433,7 +436,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_seed_off.data(), d_seed_off, ((size_t)p->d.n_img + 1) * 4,
                                cudaMemcpyDeviceToHost, s));
   WS_CUDA(ctx, cudaStreamSynchronize(s));
-  p->stats[0] = p->h_ctrl[FC_SWEEPS];
+  p->stats[0] = p->h_ctrl[FC_STALE];
   if (p->merged) p->stats[3] = p->h_ctrl[FC_WORDS + 1];
   p->stats[1] = p->h_ctrl[FC_ACTIVATIONS];
   p->stats[2] = p->h_ctrl[FC_JUMP_ROUNDS];
@@ -442,6 +445,13 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   if (err & 1u) return fail(ctx, WS_ERR_SEED_OOB, "a seed lies outside the image");
   if (err & 2u) return fail(ctx, WS_ERR_HOP_OVERFLOW, ws_status_str(WS_ERR_HOP_OVERFLOW));
   if (err & 4u) return fail(ctx, WS_ERR_INTERNAL, "flood did not reach a fixed point");
+  if (err & 8u) {
+    char msg[256];
+    snprintf(msg, sizeof msg, "flood worklist: a claimed slot was never written (bucket %u slot %u tail %u head %u avail %d cap %u outstanding %u now 0x%x)",
+             p->h_ctrl[16], p->h_ctrl[17], p->h_ctrl[18], p->h_ctrl[19], (int)p->h_ctrl[20], p->h_ctrl[21], p->h_ctrl[22], p->h_ctrl[23]);
+    return fail(ctx, WS_ERR_INTERNAL, msg);
+  }
+  if (err & 16u) return fail(ctx, WS_ERR_INTERNAL, "flood worklist watchdog fired");
   p->ran = true;
   return WS_OK;
 }
@@ -543,12 +553,19 @@ ws_status check_flood_errors(ws_plan* p) {
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl, p->fb.ctrl, FC_WORDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  p->stats[0] += p->h_ctrl[FC_SWEEPS];
+  p->stats[0] += p->h_ctrl[FC_STALE];
   p->stats[1] += p->h_ctrl[FC_ACTIVATIONS];
   const uint32_t err = p->h_ctrl[FC_ERROR];
   if (err & 1u) return fail(ctx, WS_ERR_SEED_OOB, "a seed lies outside the strip");
   if (err & 2u) return fail(ctx, WS_ERR_HOP_OVERFLOW, ws_status_str(WS_ERR_HOP_OVERFLOW));
   if (err & 4u) return fail(ctx, WS_ERR_INTERNAL, "flood did not reach a fixed point");
+  if (err & 8u) {
+    char msg[256];
+    snprintf(msg, sizeof msg, "flood worklist: a claimed slot was never written (bucket %u slot %u tail %u head %u avail %d cap %u outstanding %u now 0x%x)",
+             p->h_ctrl[16], p->h_ctrl[17], p->h_ctrl[18], p->h_ctrl[19], (int)p->h_ctrl[20], p->h_ctrl[21], p->h_ctrl[22], p->h_ctrl[23]);
+    return fail(ctx, WS_ERR_INTERNAL, msg);
+  }
+  if (err & 16u) return fail(ctx, WS_ERR_INTERNAL, "flood worklist watchdog fired");
   return WS_OK;
 }
 int first_owned(const ws_plan* p) { return p->d.halo_top ? 1 : 0; }
@@ -586,7 +603,8 @@ extern "C" ws_status ws_plan_strip_begin(ws_plan* p, const ws_config* cfg, const
   const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_img, cfg->max_water_level, s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, p->d_strip_off, (uint32_t)nseeds, st->colour_base, s));
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, ctx->flood_grid, s));
+  p->bucket_shift = flood_bucket_shift(nseeds, p->d);
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, s));
   p->stats[4] += 3;
   return check_flood_errors(p);
 }
@@ -608,15 +626,14 @@ extern "C" ws_status ws_plan_strip_import_times(ws_plan* p, const uint32_t* d_to
   *changed = 0;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  // fresh worklists; keep the error word
+  // the worklist is empty after a completed flood; reset the statistics, keep the error word
   WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl, 0, sizeof(uint32_t) * FC_ERROR, s));
   WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl + FC_STRIP_CHANGED, 0, sizeof(uint32_t), s));
-  WS_CUDA(ctx, cudaMemsetAsync(p->fb.flags, 0, sizeof(uint32_t) * (size_t)p->d.tiles_total(), s));
-  if (d_top && p->d.halo_top) WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, 0, 1, d_top, s));
+  if (d_top && p->d.halo_top) WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, 0, 1, d_top, p->bucket_shift, s));
   if (d_bottom && p->d.halo_bottom)
-    WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, p->d.rows - 1, p->d.rows - 2, d_bottom, s));
+    WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, p->d.rows - 1, p->d.rows - 2, d_bottom, p->bucket_shift, s));
   const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, ctx->flood_grid, s));  // returns at once if nothing woke up
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, s));  // returns at once if nothing woke up
   p->stats[4] += 3;
   WS_TRY(check_flood_errors(p));
   *changed = p->h_ctrl[FC_STRIP_CHANGED] ? 1 : 0;

@@ -6,21 +6,22 @@
 // encoding and DESIGN.md section 2 for why any relaxation order gives the reference's result.
 //
 // Kernel structure (sm_100a):
-//   * persistent cooperative grid, one worklist of active tiles per sweep, grid barrier
-//     between sweeps, three rotating lists so pushes never race with the reset;
-//   * every CTA = 8 consumer warps + 1 producer warp.  The producer hands out tiles
-//     (atomic cursor), stages each tile's 34 x 72-word box of arrival times and its
-//     32 x 64 image bytes with the bulk-copy engine (cp.async.bulk -> SASS UBLKCP, completion
-//     on an mbarrier) into a two-stage ring, and afterwards publishes the tile's neighbours
-//     to the next worklist.  The consumers therefore never wait on a global round trip:
-//     they copy the stage into an odd-stride working tile and iterate on it;
+//   * persistent grid (one CTA slot per co-resident CTA), NO grid barrier: an asynchronous worklist of
+//     active tiles, bucketed by the water level of the wake-up.  Every CTA always takes the tile with
+//     the lowest bucket that is available, so tiles run roughly in the order of the reference's level
+//     loop and rarely iterate on values a lower level overwrites later (a level-blind FIFO of sweeps
+//     re-ran every tile ~9-12 times on smooth fields; this order needs ~4).  The flood ends when the
+//     count of queued + in-flight entries reaches zero;
+//   * every CTA = 8 consumer warps + 1 producer warp.  The producer claims tiles, stages each tile's
+//     34 x 72-word box of arrival times and its 32 x 64 image bytes with the bulk-copy engine
+//     (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) into a two-stage ring, and afterwards
+//     publishes the tile's neighbours to the worklist.  The consumers never wait on a global round
+//     trip: they copy the stage into an odd-stride working tile and iterate on it;
 //   * the in-tile iteration alternates column and row ownership (8 pixels of Gauss-Seidel
-//     along the phase's axis per step) until a phase changes nothing.
+//     along the phase's axis per step) until a phase changes nothing;
+//   * results go back with atomicMin: two CTAs may (rarely) hold the same tile at once, and arrival
+//     times must never go up.
 #include "kernels.cuh"
-
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 #ifndef WS_FLOOD_BULK
 #define WS_FLOOD_BULK 3
@@ -54,6 +55,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0u;
 }
 // global -> shared bulk copy (16-byte aligned, multiple of 16 bytes), completes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -129,18 +141,57 @@ cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, u
   fill_state_kernel<<<148 * 16, 256, 0, s>>>(b, d, img, lmax);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(b.flags, 0, sizeof(uint32_t) * (size_t)d.tiles_total(), s);
+  // empty worklist: all ring slots unwritten, no tile queued, counters zero
+  e = cudaMemsetAsync(b.qslots, 0xFF, sizeof(uint32_t) * (size_t)FLOOD_BUCKETS * b.qcap, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(b.qmask, 0, sizeof(unsigned long long) * (size_t)d.tiles_total(), s);
   if (e != cudaSuccess) return e;
   return cudaMemsetAsync(b.ctrl, 0, sizeof(uint32_t) * FC_WORDS, s);
 }
 
-__device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t ntiles, int list, uint32_t tile) {
-  const uint32_t bit = 1u << list;
-  if (ld_cg(&b.flags[tile]) & bit) return;  // already queued (the common case when seeds are dense)
-  const uint32_t old = atomicOr(&b.flags[tile], bit);
-  if (!(old & bit)) {
-    const uint32_t pos = atomicAdd(&b.ctrl[FC_COUNT0 + list], 1u);
-    st_cg(&b.lists[(size_t)list * ntiles + pos], tile);
+__device__ __forceinline__ unsigned long long ld_cg64(const unsigned long long* p) { return __ldcg(p); }
+
+__device__ __forceinline__ uint32_t flood_bucket(uint32_t level, int shift) {
+  const uint32_t b = level >> shift;
+  return b < (uint32_t)FLOOD_BUCKETS ? b : (uint32_t)FLOOD_BUCKETS - 1u;
+}
+
+// Wake a tile, part 1: mark it dirty; returns true when the caller must append an entry to ring
+// `bucket` (no entry of the same or a better priority is queued).  The caller has made the data the
+// tile must see visible (fence) before this call; whoever takes an entry clears its bucket bit and
+// the dirty bit in one atomic and loads the tile afterwards.  kQuiescent: no flood kernel is running
+// (seeding, strip import), so a plain load may decide that there is nothing to do; inside the flood
+// the decision must come from an atomic on the mask word -- a read-modify-write is ordered against the
+// taker's atomicAnd, a load is not.
+template <bool kQuiescent>
+__device__ __forceinline__ bool push_mark(const FloodBuffers& b, uint32_t tile, uint32_t bucket) {
+  const unsigned long long bit = 1ull << bucket, not_worse = (bit << 1) - 1ull;
+  unsigned long long cur = 0ull;  // optimistic: the tile is idle (neither queued nor dirty)
+  if (kQuiescent) {
+    cur = ld_cg64(&b.qmask[tile]);
+    if ((cur & not_worse) && (cur & Q_DIRTY)) return false;  // the common case when seeds are dense
+  }
+  for (;;) {
+    const bool queued = (cur & not_worse) != 0ull;
+    const unsigned long long want = cur | Q_DIRTY | (queued ? 0ull : bit);
+    if (want == cur) return false;
+    const unsigned long long old = atomicCAS(&b.qmask[tile], cur, want);
+    if (old == cur) return !queued;
+    cur = old;
+  }
+}
+// part 2: reserve a slot, write it, raise the semaphore.  No fence between the two: a taker that wins a
+// slot before its tile id has landed simply waits for it (the slot holds Q_EMPTY until then).
+__device__ __forceinline__ void push_append(const FloodBuffers& b, uint32_t tile, uint32_t bucket) {
+  const uint32_t t = atomicAdd(&b.ctrl[FC_QTAIL0 + bucket], 1u);
+  st_cg(&b.qslots[(size_t)bucket * b.qcap + t % b.qcap], tile);
+  atomicAdd(&b.ctrl[FC_QAVAIL0 + bucket], 1u);
+}
+template <bool kQuiescent>
+__device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t tile, uint32_t bucket) {
+  if (push_mark<kQuiescent>(b, tile, bucket)) {
+    atomicAdd(&b.ctrl[FC_OUTSTANDING], 1u);
+    push_append(b, tile, bucket);
   }
 }
 
@@ -166,19 +217,17 @@ __global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDim
   st_cg(&b.T[(size_t)img * d.t_plane() + d.t_index((int)r, (int)c)], 0u);
   atomicMax(&b.lab[(size_t)img * d.px_per_img() + (size_t)r * d.cols + c],
             LAB_RESOLVED | (colour_base + i - __ldg(seed_off + img) + 1u));
-  // Red-black order over the tiles: the first sweep takes the even tiles (tx + ty even), the second the
-  // odd ones -- which then already see their neighbours' results, a Gauss-Seidel step at tile level
-  // that saves re-activations.  A tile's 4-neighbours have the other parity, so later sweeps alternate
-  // by themselves; only the seeding has to split the lists.
-  const uint32_t ntiles = (uint32_t)d.tiles_total();
+  // Red-black order over the tiles: the even tiles (tx + ty even) start in bucket 0, the odd ones in
+  // bucket 1 -- they then already see their neighbours' results, a Gauss-Seidel step at tile level that
+  // saves re-activations.
   const int ty = r / TILE_H, tx = c / TILE_W;
   const uint32_t tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
-  const int par = (tx + ty) & 1;
-  push_tile(b, ntiles, par, tile);
-  if (r % TILE_H == 0 && ty > 0) push_tile(b, ntiles, par ^ 1, tile - d.tiles_x);
-  if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile(b, ntiles, par ^ 1, tile + d.tiles_x);
-  if (c % TILE_W == 0 && tx > 0) push_tile(b, ntiles, par ^ 1, tile - 1);
-  if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile(b, ntiles, par ^ 1, tile + 1);
+  const uint32_t par = (uint32_t)(tx + ty) & 1u;
+  push_tile<true>(b, tile, par);  // (the flood is a later launch: no fence needed here)
+  if (r % TILE_H == 0 && ty > 0) push_tile<true>(b, tile - d.tiles_x, par ^ 1u);
+  if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile<true>(b, tile + d.tiles_x, par ^ 1u);
+  if (c % TILE_W == 0 && tx > 0) push_tile<true>(b, tile - 1, par ^ 1u);
+  if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile<true>(b, tile + 1, par ^ 1u);
 }
 
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
@@ -219,9 +268,11 @@ struct FloodArgs {
   FloodBuffers b;
   ImageDims d;
   int check_overflow;
+  int bucket_shift;  // worklist bucket = wake-up level >> bucket_shift
 };
 
-enum { EDGE_UP = 1, EDGE_DOWN = 2, EDGE_LEFT = 4, EDGE_RIGHT = 8 };
+enum { DIR_UP = 0, DIR_DOWN = 1, DIR_LEFT = 2, DIR_RIGHT = 3 };
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 
 struct FloodStage {
@@ -234,7 +285,9 @@ struct __align__(128) FloodSmem {
   uint32_t W[SM_H * SM_W];          // working tile incl. halo
   uint8_t wpix[TILE_H * PIX_W];     // working image tile
   uint64_t full[2], empty[2];       // mbarriers of the ring
-  uint32_t tile[2], edge[2];
+  uint32_t tile[2];
+  uint32_t key[2][4];               // per stage and direction: smallest value a changed edge pixel offers
+                                    // the pixel facing it (KEY_NONE: that neighbour need not re-run)
 };
 
 __device__ __forceinline__ uint32_t flood_A(uint32_t pix) { return pix == 255u ? T_INF : ((pix << 24) | 1u); }
@@ -349,32 +402,99 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
   // A neighbour tile re-runs only if a changed edge pixel can still lower the pixel facing it:
   // T(edge) + 1 < T(facing pixel), the latter as staged in our halo (never newer than the truth, so the
   // test never drops a needed wake-up).  Without it every tile woke all four neighbours, including the
-  // one its values came from, and most activations were such echoes.
-  uint32_t e = 0;
+  // one its values came from, and most activations were such echoes.  The smallest such offer per
+  // direction is the priority of the wake-up.
+  uint32_t kl = KEY_NONE, kr = KEY_NONE, ku = KEY_NONE, kd = KEY_NONE;
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     const uint32_t v = colp[i * SM_W];
     if (v != st.T[(cgp * ROWS_PER_THREAD + i + 1) * STG_W + cl + T_PAD_L]) {
-      st_cg(Tg + (size_t)i * tp, v);
-      if (cl == 0 && v + 1u < colp[i * SM_W - 1]) e |= EDGE_LEFT;
-      if (cl == TILE_W - 1 && v + 1u < colp[i * SM_W + 1]) e |= EDGE_RIGHT;
-      if (cgp == 0 && i == 0 && v + 1u < colp[-SM_W]) e |= EDGE_UP;
+      atomicMin(Tg + (size_t)i * tp, v);  // result unused: a fire-and-forget RED.MIN (measured: same time as st)
+      if (cl == 0 && v + 1u < colp[i * SM_W - 1]) kl = min(kl, v + 1u);
+      if (cl == TILE_W - 1 && v + 1u < colp[i * SM_W + 1]) kr = min(kr, v + 1u);
+      if (cgp == 0 && i == 0 && v + 1u < colp[-SM_W]) ku = v + 1u;
       if (cgp == TILE_H / ROWS_PER_THREAD - 1 && i == ROWS_PER_THREAD - 1 && v + 1u < colp[ROWS_PER_THREAD * SM_W])
-        e |= EDGE_DOWN;
+        kd = v + 1u;
     }
   }
-  if (e) atomicOr(&sm.edge[s], e);
+  if (kl != KEY_NONE) atomicMin(&sm.key[s][DIR_LEFT], kl);
+  if (kr != KEY_NONE) atomicMin(&sm.key[s][DIR_RIGHT], kr);
+  if (ku != KEY_NONE) atomicMin(&sm.key[s][DIR_UP], ku);
+  if (kd != KEY_NONE) atomicMin(&sm.key[s][DIR_DOWN], kd);
   if (tid == 0) atomicAdd(&a.b.ctrl[FC_PHASES], nphase);
   if (a.check_overflow && ovf) atomicOr(&a.b.ctrl[FC_ERROR], 2u);
 }
 
-// Persistent cooperative kernel.  Sweep k drains worklist k%3, fills worklist (k+1)%3 and resets
-// worklist (k+2)%3; one grid barrier per sweep; ends when a sweep starts with an empty list.
+// ---- producer side: the worklist -----------------------------------------------------------
+
+constexpr int POP_MAX = 4;  // tiles one claim may take when the worklist is long
+
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Claim tiles from the best (lowest) non-empty bucket (warp-collective): up to POP_MAX when that
+// bucket holds far more entries than there are CTAs -- the claim is a chain of five dependent L2 round
+// trips, and on noise fields, where every tile is queued at once, that chain, not the iteration, would
+// bound the kernel -- otherwise one.  Returns the number claimed (0: nothing available right now);
+// lane j < n holds the j-th tile in `mine`.
+__device__ __forceinline__ int flood_pop(const FloodBuffers& b, int lane, uint32_t& mine) {
+  for (;;) {
+    const int a0 = (int)ld_poll(&b.ctrl[FC_QAVAIL0 + lane]);
+    const int a1 = (int)ld_poll(&b.ctrl[FC_QAVAIL0 + 32 + lane]);
+    const uint32_t m0 = __ballot_sync(0xffffffffu, a0 > 0), m1 = __ballot_sync(0xffffffffu, a1 > 0);
+    if ((m0 | m1) == 0u) return 0;
+    const int bk = m0 ? __ffs((int)m0) - 1 : 31 + __ffs((int)m1);
+    const int av = __shfl_sync(0xffffffffu, bk < 32 ? a0 : a1, bk & 31);
+    int want = av / (int)(2u * gridDim.x);
+    want = want < 1 ? 1 : (want > POP_MAX ? POP_MAX : want);
+    int got = 0;
+    uint32_t h0 = 0;
+    if (lane == 0) {
+      // the semaphore guarantees a reserved slot for every unit of a successful decrement
+      const int old = (int)atomicSub(&b.ctrl[FC_QAVAIL0 + bk], (uint32_t)want);
+      got = old <= 0 ? 0 : (old < want ? old : want);
+      if (got < want) atomicAdd(&b.ctrl[FC_QAVAIL0 + bk], (uint32_t)(want - got));  // lost (part of) the race
+      if (got) h0 = atomicAdd(&b.ctrl[FC_QHEAD0 + bk], (uint32_t)got);
+    }
+    got = __shfl_sync(0xffffffffu, got, 0);
+    h0 = __shfl_sync(0xffffffffu, h0, 0);
+    if (got == 0) continue;
+    uint32_t v = Q_EMPTY;
+    bool valid = false;
+    if (lane < got) {
+      uint32_t* slot = &b.qslots[(size_t)bk * b.qcap + (h0 + (uint32_t)lane) % b.qcap];
+      v = ld_poll(slot);
+      // the slot may belong to a push that has reserved it and is about to write it
+      for (uint32_t spin = 0; v == Q_EMPTY && spin < (1u << 22); ++spin) v = ld_poll(slot);
+      if (v == Q_EMPTY) {
+        atomicOr(&b.ctrl[FC_ERROR], 8u);
+      } else {
+        st_cg(slot, Q_EMPTY);
+        const unsigned long long old = atomicAnd(&b.qmask[v], ~((1ull << bk) | Q_DIRTY));
+        valid = (old & Q_DIRTY) != 0ull;  // else: already served through a better bucket since it was queued
+      }
+    }
+    const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+    const int nvalid = __popc(vm);
+    if (lane == 0 && nvalid < got) {
+      atomicSub(&b.ctrl[FC_OUTSTANDING], (uint32_t)(got - nvalid));
+      atomicAdd(&b.ctrl[FC_STALE], (uint32_t)(got - nvalid));
+    }
+    if (nvalid == 0) continue;
+    mine = TILE_NONE;
+#pragma unroll
+    for (int j = 0; j < POP_MAX; ++j) {
+      const uint32_t src = __fns(vm, 0, j + 1);  // lane of the j-th valid claim
+      const uint32_t t = __shfl_sync(0xffffffffu, v, (int)(src & 31u));
+      if (lane == j && src != 0xffffffffu) mine = t;
+    }
+    return nvalid;
+  }
+}
+
+// Persistent kernel, no grid barrier.  See the head of this file.
 __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(FloodArgs a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ FloodSmem sm;
   const ImageDims& d = a.d;
-  const uint32_t ntiles = (uint32_t)d.tiles_total();
   const bool producer = threadIdx.x >= FLOOD_CONSUMERS;
   const int lane = threadIdx.x & 31;
 
@@ -387,140 +507,144 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(FloodArgs a) {
   }
   __syncthreads();
 
-  uint32_t slot = 0;  // ring slots used so far (same sequence on both sides); stage = slot & 1
-  int cur = 0;
-  for (uint32_t sweep = 0;; ++sweep) {
-    const uint32_t n = ld_cg(&a.b.ctrl[FC_COUNT0 + cur]);
-    // an empty list ends the flood -- except the very first one (even tiles), after which the odd
-    // tiles seeded into list 1 still have to run
-    if (n == 0 && (sweep > 0 || ld_cg(&a.b.ctrl[FC_COUNT0 + 1]) == 0)) break;
-    const int nxt = (cur + 1) % 3, old = (cur + 2) % 3;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      st_cg(&a.b.ctrl[FC_COUNT0 + old], 0u);
-      st_cg(&a.b.ctrl[FC_CURSOR0 + old], 0u);
-      atomicAdd(&a.b.ctrl[FC_SWEEPS], 1u);
-    }
-
-    if (producer) {
-      // =========================== producer warp ============================================
-      bool pending[2] = {false, false};
-      // Publish the neighbours of the tile that last used stage s (after its consumers released it).
-      auto retire = [&](int s, uint32_t use_idx) {
-        mbar_wait(&sm.empty[s], use_idx & 1u);
-        const uint32_t tile = sm.tile[s];
-        const uint32_t e = sm.edge[s];
-        if (e) {
-          const int trem = tile % d.tiles_per_img();
-          const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
-          __threadfence();  // the consumers' stores (ordered before us by the mbarrier) before the pushes
-          if (lane == 0 && (e & EDGE_UP) && ty > 0) push_tile(a.b, ntiles, nxt, tile - d.tiles_x);
-          if (lane == 1 && (e & EDGE_DOWN) && ty + 1 < d.tiles_y) push_tile(a.b, ntiles, nxt, tile + d.tiles_x);
-          if (lane == 2 && (e & EDGE_LEFT) && tx > 0) push_tile(a.b, ntiles, nxt, tile - 1);
-          if (lane == 3 && (e & EDGE_RIGHT) && tx + 1 < d.tiles_x) push_tile(a.b, ntiles, nxt, tile + 1);
+  if (producer) {
+    // =========================== producer warp ============================================
+    bool pending[2] = {false, false};
+    uint32_t uses[2] = {0u, 0u};  // tiles staged into each stage so far
+    uint32_t q_tile = TILE_NONE;  // lane j: j-th tile of the last claim
+    int q_n = 0, q_i = 0;         // tiles claimed / already handed to a stage
+    // Publish the neighbours of the tile that used stage s; its consumers have released the stage.
+    auto retire = [&](int s) {
+      const uint32_t tile = sm.tile[s];
+      const uint32_t k = lane < 4 ? sm.key[s][lane] : KEY_NONE;
+      const uint32_t km = __ballot_sync(0xffffffffu, k != KEY_NONE);
+      if (km) {
+        const int trem = tile % d.tiles_per_img();
+        const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
+        // Count the entries we may add BEFORE any of them can be taken (the count must never read 0
+        // while work exists); the fence orders that, and the consumers' results (ordered before us by
+        // the mbarrier), before the marks and appends below.  The surplus is returned afterwards.
+        if (lane == 0) atomicAdd(&a.b.ctrl[FC_OUTSTANDING], 3u);  // + 4 possible entries - this tile
+        fence_acq_rel_gpu();
+        const uint32_t bk = flood_bucket(k >> 24, a.bucket_shift);
+        uint32_t nb = TILE_NONE;
+        if (k != KEY_NONE) {
+          if (lane == DIR_UP && ty > 0) nb = tile - d.tiles_x;
+          if (lane == DIR_DOWN && ty + 1 < d.tiles_y) nb = tile + d.tiles_x;
+          if (lane == DIR_LEFT && tx > 0) nb = tile - 1;
+          if (lane == DIR_RIGHT && tx + 1 < d.tiles_x) nb = tile + 1;
+        }
+        const bool app = nb != TILE_NONE && push_mark<false>(a.b, nb, bk);
+        if (app) push_append(a.b, nb, bk);
+        const int n = __popc(__ballot_sync(0xffffffffu, app));
+        if (lane == 0 && n < 4) atomicSub(&a.b.ctrl[FC_OUTSTANDING], (uint32_t)(4 - n));
+      } else {
+        if (lane == 0) atomicSub(&a.b.ctrl[FC_OUTSTANDING], 1u);
+      }
+      pending[s] = false;
+    };
+    for (uint32_t slot = 0;; ++slot) {
+      const int s = slot & 1;
+      if (pending[s]) {  // the stage is reused: wait for its consumers, publish its tile
+        mbar_wait(&sm.empty[s], (uses[s] - 1u) & 1u);
+        retire(s);
+      }
+      // claim a tile; while there is none, finish the other stage (its pushes may be the next work)
+      uint32_t tile = TILE_NONE;
+      uint32_t idle = 0;
+      for (;;) {
+        if (q_i == q_n) {
+          q_n = flood_pop(a.b, lane, q_tile);
+          q_i = 0;
+        }
+        if (q_i < q_n) {
+          tile = __shfl_sync(0xffffffffu, q_tile, q_i);
+          ++q_i;
+          break;
+        }
+        if (pending[s ^ 1]) {
+          if (mbar_test(&sm.empty[s ^ 1], (uses[s ^ 1] - 1u) & 1u)) {
+            retire(s ^ 1);
+            continue;
+          }
+        } else if (ld_poll(&a.b.ctrl[FC_OUTSTANDING]) == 0u || (ld_poll(&a.b.ctrl[FC_ERROR]) & 24u)) {
+          break;  // nothing queued, nothing in flight anywhere: the fixed point is reached
+        }
+        __nanosleep(100);
+        if (++idle > (1u << 25)) atomicOr(&a.b.ctrl[FC_ERROR], 16u);  // watchdog (> 10 s idle): never hang the device
+      }
+      if (lane == 0) {
+        if (idle) atomicAdd(&a.b.ctrl[FC_IDLE], idle);
+        sm.tile[s] = tile;
+        sm.key[s][0] = sm.key[s][1] = sm.key[s][2] = sm.key[s][3] = KEY_NONE;
+      }
+      if (tile == TILE_NONE) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.full[s]);
+        break;
+      }
+      if (lane == 0) atomicAdd(&a.b.ctrl[FC_ACTIVATIONS], 1u);
+      {
+        // bisect switch: bit 0 = arrival times by bulk copy, bit 1 = image bytes by bulk copy
+        constexpr bool BULK_T = (WS_FLOOD_BULK & 1) != 0, BULK_P = (WS_FLOOD_BULK & 2) != 0;
+        constexpr uint32_t TX = (BULK_T ? STG_H * STG_W * 4 : 0) + (BULK_P ? TILE_H * TILE_W : 0);
+        const int tpi = d.tiles_per_img();
+        const int img = tile / tpi;
+        const int trem = tile - img * tpi;
+        const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
+        // box rows r0-1 .. r0+32 (padded row index r0 .. r0+33), columns c0-4 .. c0+67 (padded c0 .. c0+71)
+        const uint32_t* tsrc = a.b.T + (size_t)img * d.t_plane() + (size_t)(ty * TILE_H) * d.t_pitch() + tx * TILE_W;
+        const uint8_t* psrc = a.b.pix + (size_t)img * d.pix_plane() + (size_t)(ty * TILE_H) * d.pix_pitch() + tx * TILE_W;
+        fence_acq_rel_gpu();  // the claim (atomic on the tile's mask word) before the loads of the tile
+        if (!BULK_T) {
+          for (int i = lane; i < STG_H * STG_W; i += 32) {
+            const int r = i / STG_W, c = i - r * STG_W;
+            sm.st[s].T[i] = ld_cg(tsrc + (size_t)r * d.t_pitch() + c);
+          }
+        }
+        if (!BULK_P) {
+          for (int i = lane; i < TILE_H * TILE_W; i += 32) {
+            const int r = i / TILE_W, c = i - r * TILE_W;
+            sm.st[s].pix[i] = psrc[(size_t)r * d.pix_pitch() + c];
+          }
         }
         __syncwarp();
-      };
-      for (;;) {
-        const int s = slot & 1;
-        if (pending[s]) {
-          retire(s, (slot >> 1) - 1u);
-          pending[s] = false;
-        } else if (slot >= 2) {
-          mbar_wait(&sm.empty[s], ((slot >> 1) - 1u) & 1u);  // a "no more tiles" slot: just keep the phases aligned
-        }
-        uint32_t tile = TILE_NONE;
         if (lane == 0) {
-          const uint32_t k = atomicAdd(&a.b.ctrl[FC_CURSOR0 + cur], 1u);
-          if (k < n) {
-            tile = ld_cg(&a.b.lists[(size_t)cur * ntiles + k]);
-            atomicAnd(&a.b.flags[tile], ~(1u << cur));
-            atomicAdd(&a.b.ctrl[FC_ACTIVATIONS], 1u);
-          }
-          sm.tile[s] = tile;
-          sm.edge[s] = 0u;
+          if (TX) mbar_arrive_expect_tx(&sm.full[s], TX); else mbar_arrive(&sm.full[s]);
         }
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile == TILE_NONE) {
-          if (lane == 0) mbar_arrive(&sm.full[s]);
-          ++slot;
-          break;
+        __syncwarp();
+        // The tile's pixels were last written through the generic proxy (atomics / st.global by consumer
+        // threads, possibly of other CTAs, ordered before us by the worklist atomics); the bulk copies
+        // read them through the async proxy.  Every issuing lane needs the cross-proxy fence.
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        // cp.async.bulk is issued from the warp's UNIFORM datapath (SASS: ELECT + R2UR + UBLKCP in a
+        // waterfall loop over the lanes).  Letting lanes issue different rows made two such loops run
+        // on divergent halves of the warp at once, and they clobbered each other's uniform registers
+        // (observed: rows landing late / in the wrong place).  One lane issues every row.
+        if (lane == 0) {
+          if (BULK_T)
+            for (int r = 0; r < STG_H; ++r)
+              bulk_g2s(&sm.st[s].T[r * STG_W], tsrc + (size_t)r * d.t_pitch(), STG_W * 4, &sm.full[s]);
+          if (BULK_P)
+            for (int r = 0; r < TILE_H; ++r)
+              bulk_g2s(&sm.st[s].pix[r * TILE_W], psrc + (size_t)r * d.pix_pitch(), TILE_W, &sm.full[s]);
         }
-        {
-          // bisect switch: bit 0 = arrival times by bulk copy, bit 1 = image bytes by bulk copy
-          constexpr bool BULK_T = (WS_FLOOD_BULK & 1) != 0, BULK_P = (WS_FLOOD_BULK & 2) != 0;
-          constexpr uint32_t TX = (BULK_T ? STG_H * STG_W * 4 : 0) + (BULK_P ? TILE_H * TILE_W : 0);
-          const int tpi = d.tiles_per_img();
-          const int img = tile / tpi;
-          const int trem = tile - img * tpi;
-          const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
-          // box rows r0-1 .. r0+32 (padded row index r0 .. r0+33), columns c0-4 .. c0+67 (padded c0 .. c0+71)
-          const uint32_t* tsrc = a.b.T + (size_t)img * d.t_plane() + (size_t)(ty * TILE_H) * d.t_pitch() + tx * TILE_W;
-          const uint8_t* psrc = a.b.pix + (size_t)img * d.pix_plane() + (size_t)(ty * TILE_H) * d.pix_pitch() + tx * TILE_W;
-          if (!BULK_T) {
-            for (int i = lane; i < STG_H * STG_W; i += 32) {
-              const int r = i / STG_W, c = i - r * STG_W;
-              sm.st[s].T[i] = ld_cg(tsrc + (size_t)r * d.t_pitch() + c);
-            }
-          }
-          if (!BULK_P) {
-            for (int i = lane; i < TILE_H * TILE_W; i += 32) {
-              const int r = i / TILE_W, c = i - r * TILE_W;
-              sm.st[s].pix[i] = psrc[(size_t)r * d.pix_pitch() + c];
-            }
-          }
-          __syncwarp();
-          if (lane == 0) {
-            if (TX) mbar_arrive_expect_tx(&sm.full[s], TX); else mbar_arrive(&sm.full[s]);
-          }
-          __syncwarp();
-          // The tile's pixels were last written through the generic proxy (st.global by consumer
-          // threads, possibly of other CTAs, ordered before us by the grid barrier); the bulk copies
-          // read them through the async proxy.  Every issuing lane needs the cross-proxy fence.
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-          // cp.async.bulk is issued from the warp's UNIFORM datapath (SASS: ELECT + R2UR + UBLKCP in a
-          // waterfall loop over the lanes).  Letting lanes issue different rows made two such loops run
-          // on divergent halves of the warp at once, and they clobbered each other's uniform registers
-          // (observed: rows landing late / in the wrong place).  One lane issues every row.
-          if (lane == 0) {
-            if (BULK_T)
-              for (int r = 0; r < STG_H; ++r)
-                bulk_g2s(&sm.st[s].T[r * STG_W], tsrc + (size_t)r * d.t_pitch(), STG_W * 4, &sm.full[s]);
-            if (BULK_P)
-              for (int r = 0; r < TILE_H; ++r)
-                bulk_g2s(&sm.st[s].pix[r * TILE_W], psrc + (size_t)r * d.pix_pitch(), TILE_W, &sm.full[s]);
-          }
-          __syncwarp();
-        }
-        pending[s] = true;
-        ++slot;
+        __syncwarp();
       }
-      // drain: the slot before the terminating one may still be in flight; then the terminator's ack
-      {
-        const uint32_t last = slot - 1;        // the "no more tiles" slot
-        const int so = (last & 1) ^ 1;
-        if (pending[so]) retire(so, (last - 1) >> 1);
-        mbar_wait(&sm.empty[last & 1], (last >> 1) & 1u);
-      }
-    } else {
-      // =========================== consumer warps ===========================================
-      for (;;) {
-        const int s = slot & 1;
-        mbar_wait(&sm.full[s], (slot >> 1) & 1u);
-        const uint32_t tile = sm.tile[s];
-        ++slot;
-        if (tile == TILE_NONE) {
-          consumer_sync();
-          if (threadIdx.x == 0) mbar_arrive(&sm.empty[s]);
-          break;
-        }
-        flood_consume(a, sm, s, tile);
-        consumer_sync();  // all stores of the tile issued, all reads of the stage done
-        if (threadIdx.x == 0) mbar_arrive(&sm.empty[s]);
-      }
+      pending[s] = true;
+      ++uses[s];
     }
-    __syncthreads();
-    grid.sync();
-    cur = nxt;
+  } else {
+    // =========================== consumer warps ===========================================
+    for (uint32_t slot = 0;; ++slot) {
+      const int s = slot & 1;
+      mbar_wait(&sm.full[s], (slot >> 1) & 1u);
+      const uint32_t tile = sm.tile[s];
+      if (tile == TILE_NONE) break;
+      flood_consume(a, sm, s, tile);
+      consumer_sync();  // all results of the tile issued, all reads of the stage done
+      if (threadIdx.x == 0) mbar_arrive(&sm.empty[s]);
+    }
   }
 }
 
@@ -533,12 +657,26 @@ static int coop_max_grid_flood(int device) {
 
 int flood_max_grid(int device) { return coop_max_grid_flood(device); }
 
-cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int grid, cudaStream_t s) {
-  FloodArgs a{b, d, check_overflow};
-  void* args[] = {&a};
+// Granularity of the worklist's priority.  Fields whose structures are much larger than a tile (few
+// seeds per tile) have long-range dependencies: fine buckets (4 levels) keep the tiles in the order of
+// the reference's level loop and save most re-activations.  On noise-like fields (many seeds per tile)
+// everything is local, a tile's wake-ups come from all sides at unrelated levels, and it pays to let
+// them accumulate: coarse buckets (32 levels).  Either choice gives the same result, only the number of
+// tile activations differs.
+int flood_bucket_shift(size_t nseeds, const ImageDims& d) {
+  const size_t tiles = (size_t)d.tiles_total();
+  return nseeds >= 4 * tiles ? 5 : 2;
+}
+
+// The grid never exceeds the co-resident CTA count; no CTA waits for a particular other CTA (only for
+// the worklist to drain), so a plain launch is enough.
+cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int bucket_shift, int grid,
+                         cudaStream_t s) {
+  FloodArgs a{b, d, check_overflow, bucket_shift};
   const int want = d.tiles_total();
   const int g = want < grid ? (want > 0 ? want : 1) : grid;
-  return cudaLaunchCooperativeKernel((const void*)flood_kernel, dim3(g), dim3(FLOOD_THREADS), args, 0, s);
+  flood_kernel<<<g, FLOOD_THREADS, 0, s>>>(a);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
@@ -605,7 +743,7 @@ __global__ void __launch_bounds__(256) strip_export_T_kernel(const uint32_t* __r
 // min-merge a neighbour's row into halo row `row`; where it got lower, wake the tile that holds the
 // adjacent owned row `nb_row`
 __global__ void __launch_bounds__(256) strip_import_T_kernel(FloodBuffers b, ImageDims d, int row, int nb_row,
-                                                             const uint32_t* __restrict__ in) {
+                                                             const uint32_t* __restrict__ in, int bucket_shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d.cols) return;
   const uint32_t v = in[c];
@@ -613,7 +751,8 @@ __global__ void __launch_bounds__(256) strip_import_T_kernel(FloodBuffers b, Ima
   if (v < ld_cg(t)) {
     st_cg(t, v);
     atomicOr(&b.ctrl[FC_STRIP_CHANGED], 1u);
-    push_tile(b, (uint32_t)d.tiles_total(), 0, (uint32_t)((nb_row / TILE_H) * d.tiles_x + c / TILE_W));
+    __threadfence();
+    push_tile<true>(b, (uint32_t)((nb_row / TILE_H) * d.tiles_x + c / TILE_W), flood_bucket((v + 1u) >> 24, bucket_shift));
   }
 }
 
@@ -654,8 +793,8 @@ cudaError_t launch_strip_export_T(const uint32_t* T, ImageDims d, int ra, int rb
   return cudaGetLastError();
 }
 cudaError_t launch_strip_import_T(FloodBuffers b, ImageDims d, int row, int nb_row, const uint32_t* in,
-                                  cudaStream_t s) {
-  strip_import_T_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(b, d, row, nb_row, in);
+                                  int bucket_shift, cudaStream_t s) {
+  strip_import_T_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(b, d, row, nb_row, in, bucket_shift);
   return cudaGetLastError();
 }
 cudaError_t launch_strip_export_lab(const uint32_t* lab, ImageDims d, int ra, int rb, uint32_t* out_a,

@@ -6,30 +6,43 @@
 
 namespace ws {
 
-// Persistent-kernel control block of the flood (device memory, u32 words).
+// Control block of the flood and of the label kernels (device memory, u32 words).
 enum FloodCtrl {
-  FC_COUNT0 = 0,   // [0..2] entries in worklist 0/1/2
-  FC_CURSOR0 = 3,  // [3..5] next entry to hand out
-  FC_SWEEPS = 6,
-  FC_ACTIVATIONS = 7,
-  FC_ERROR = 8,    // bit 0: seed out of bounds, bit 1: hop overflow, bit 2: orphan pixel
-  FC_JUMP_FLAG0 = 9,  // [9..11] rotating "still unresolved" flags of the pointer jumping
+  FC_ACTIVATIONS = 0,  // tiles taken from the worklist and iterated            (statistics: words 0..7 are
+  FC_PHASES = 1,       // in-tile phases run                                      reset before every flood launch
+  FC_STALE = 2,        // worklist entries dropped because nothing new had arrived  of a strip import)
+  FC_IDLE = 3,         // idle polls of the producer warps
+  FC_ERROR = 8,        // bit 0: seed out of bounds, bit 1: hop overflow, bit 2: orphan pixel, bit 3: flood watchdog
+  FC_JUMP_FLAG0 = 9,   // [9..11] rotating "still unresolved" flags of the pointer jumping
   FC_JUMP_ROUNDS = 12,
   FC_STRIP_CHANGED = 13,  // a halo row of arrival times got lower on import
   FC_STRIP_PENDING = 14,  // owned pixels whose label is still a pointer
-  FC_PHASES = 15,         // in-tile phases run (diagnostic)
-  FC_WORDS = 16
+  FC_OUTSTANDING = 15,    // worklist entries queued or being processed; the flood ends when it reaches 0
+  FC_QAVAIL0 = 64,        // [64]  per bucket: entries fully published and not yet claimed (a semaphore)
+  FC_QHEAD0 = 128,        // [64]  per bucket: next slot to hand out
+  FC_QTAIL0 = 192,        // [64]  per bucket: next slot to fill
+  FC_WORDS = 256
 };
+
+// Worklist of the flood: FLOOD_BUCKETS FIFO rings of tile ids, bucket = (water level of the wake-up) >> shift.
+// Tiles are always taken from the lowest non-empty bucket, i.e. roughly in the order in which the
+// reference's level loop would reach them, which is what keeps a tile from being iterated on values
+// that a lower level is going to overwrite.
+constexpr int FLOOD_BUCKETS = 63;
+constexpr uint32_t Q_EMPTY = 0xFFFFFFFFu;
+constexpr unsigned long long Q_DIRTY = 1ull << 63;  // qmask bit: a neighbour changed since the tile was last taken
 
 struct FloodBuffers {
   uint32_t* T;       // [n_img][t_rows][t_pitch] arrival times, padded layout (common.cuh)
   uint8_t* pix;      // [n_img][pix_rows][pix_pitch] image bytes re-encoded for the flood (255 = never floods)
   uint32_t* lab;     // [px_total] label / parent words
   uint8_t* lvl;      // [px_total] level of colouring
-  uint32_t* lists;   // [3][tiles_total] worklists
-  uint32_t* flags;   // [tiles_total] bit k = queued in list k
+  uint32_t* qslots;  // [FLOOD_BUCKETS][qcap] ring buffers of tile ids, Q_EMPTY = not written yet
+  unsigned long long* qmask;  // [tiles_total] bit b: an entry for the tile sits in bucket b; bit 63: Q_DIRTY
   uint32_t* ctrl;    // [FC_WORDS]
+  uint32_t qcap;     // slots per ring = tiles_total + FLOOD_QSLACK
 };
+constexpr uint32_t FLOOD_QSLACK = 4096;  // > CTAs that can sit between claiming a slot and clearing it
 
 // Number of co-resident CTAs a cooperative launch of each persistent kernel may use.
 int flood_max_grid(int device);
@@ -54,7 +67,7 @@ cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_
 cudaError_t launch_strip_export_T(const uint32_t* T, ImageDims d, int ra, int rb, uint32_t* out_a, uint32_t* out_b,
                                   cudaStream_t s);
 cudaError_t launch_strip_import_T(FloodBuffers b, ImageDims d, int row, int nb_row, const uint32_t* in,
-                                  cudaStream_t s);
+                                  int bucket_shift, cudaStream_t s);
 cudaError_t launch_strip_export_lab(const uint32_t* lab, ImageDims d, int ra, int rb, uint32_t* out_a,
                                     uint32_t* out_b, cudaStream_t s);
 cudaError_t launch_strip_import_lab(uint32_t* lab, ImageDims d, int row, const uint32_t* in, cudaStream_t s);
@@ -62,7 +75,9 @@ cudaError_t launch_strip_count_pending(const uint32_t* lab, ImageDims d, int r0,
                                        cudaStream_t s);
 cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseeds, size_t rows, size_t cols,
                                  cudaStream_t s);
-cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int grid, cudaStream_t s);
+// bucket_shift: worklist bucket = wake-up level >> shift (flood_bucket_shift() picks it per run)
+cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int bucket_shift, int grid, cudaStream_t s);
+int flood_bucket_shift(size_t nseeds, const ImageDims& d);
 cudaError_t launch_unpad_T(const uint32_t* Tp, ImageDims d, uint32_t* out, cudaStream_t s);
 
 // --- labels (colour decision of lib.rs:235-255 with the `col0` tie-break) ---

@@ -114,7 +114,7 @@ def test_arrival_times_match_reference_loop(ws, oracle, name):
     exp = (ref.lvl.astype(np.uint32) << 24) | ref.hop
     exp[ref.lvl == 255] = 0xFF000000
     assert np.array_equal(np.minimum(T, 0xFF000000), exp)
-    assert stats["flood_sweeps"] >= 1 and stats["kernel_launches"] >= 5
+    assert stats["tile_activations"] >= 1 and stats["kernel_launches"] >= 5
 
 
 @pytest.mark.parametrize("name", ["uniform_64", "smooth_wide", "obstacles", "tiny_3x3"])
