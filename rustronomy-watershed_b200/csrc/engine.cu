@@ -68,6 +68,7 @@ struct ws_plan {
   size_t nseeds = 0;
   ws_config cfg{};
   bool ran = false, merged = false;
+  bool tree_built = false;           // hook_to / hook_lvl hold the full merge tree of the last merging run
   uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last run
 };
@@ -280,10 +281,11 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->fb.ctrl, FC_WORDS * 4);
   alloc((void**)&p->mb.level_hist, 257 * 4);
   alloc((void**)&p->mb.level_cursor, 256 * 4);
-  alloc((void**)&p->mb.red_count, 16);
+  alloc((void**)&p->mb.red_count, 64);
   alloc((void**)&p->lvl_hist, n_img * 256 * 4);
   alloc((void**)&p->d_strip_off, 16);
   alloc((void**)&p->mb.unions, n_img * 256 * 4);
+  alloc((void**)&p->mb.fin_hist, n_img * 256 * 4);
   alloc((void**)&p->mb.ndistinct, n_img * 4);
   alloc((void**)&p->mb.counts, n_img * 256 * 4);
   alloc((void**)&p->chunk_counts, minima_num_chunks(p->d) * 4);
@@ -325,6 +327,7 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->mb.hook_to);
   cudaFree(p->mb.hook_lvl);
   cudaFree(p->mb.unions);
+  cudaFree(p->mb.fin_hist);
   cudaFree(p->mb.ndistinct);
   cudaFree(p->mb.counts);
   cudaFree(p->rep);
@@ -383,16 +386,45 @@ static ws_status plan_merge(ws_plan* p) {
     WS_CUDA(ctx, cudaMalloc((void**)&p->mb.edges, cap * sizeof(uint2)));
     p->edges_cap = cap;
   }
-  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->seed_off, lmax, p->mb.red_ab, p->mb.red_w,
+  // Lake counts: only the DEFERRED edges go through the global union-find; FINAL edges are counted.
+  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->seed_off, 1, p->mb.red_ab, p->mb.red_w,
                                    p->mb.red_count, s));
-  WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, p->mb.level_hist, p->mb.level_cursor,
-                               p->mb.edges, s));
+#ifdef WS_MERGE_STATS
+  {
+    uint32_t st[16];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(st, p->mb.red_count, 64, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "merge stats: edges %u | tiles with edges %u, rounds stage0 %.2f stage1 %.2f per tile, live-edge looks "
+            "stage0 %.1f stage1 %.1f per tile, ids %.1f, out %.1f per tile\n", st[0], st[8], st[4] / (double)st[8],
+            st[5] / (double)st[8], st[6] / (double)st[8], st[7] / (double)st[8], st[9] / (double)st[8], st[10] / (double)st[8]);
+  }
+#endif
+  WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, 0, p->seed_off, p->d.n_img,
+                               p->mb.level_hist, p->mb.level_cursor, p->mb.fin_hist, p->mb.edges, s));
   WS_CUDA(ctx, launch_uf_init(p->mb, p->fb.lab, p->d, p->seeds, p->seed_off, (uint32_t)p->nseeds, s));
   WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
   WS_CUDA(ctx, launch_lake_counts(p->mb, p->d.n_img, lmax, s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
   p->stats[4] += 8;
   p->merged = true;
+  p->tree_built = false;
+  p->rep_level = -1;
+  return WS_OK;
+}
+
+// The merge tree (hook_to / hook_lvl: representative at level L = follow the links of level <= L) needs
+// the unions in level order over ALL forest edges, the tile-contracted ones included: built on the first
+// request for per-level representatives (merging snapshots, lake sizes, hooks), not for lake counts.
+static ws_status plan_build_tree(ws_plan* p) {
+  ws_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  const uint32_t lmax = p->cfg.max_water_level;
+  WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, 1, p->seed_off, p->d.n_img,
+                               p->mb.level_hist, p->mb.level_cursor, p->mb.fin_hist, p->mb.edges, s));
+  WS_CUDA(ctx, launch_uf_init(p->mb, p->fb.lab, p->d, p->seeds, p->seed_off, (uint32_t)p->nseeds, s));
+  WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
+  p->stats[4] += 6;
+  p->tree_built = true;
   p->rep_level = -1;
   return WS_OK;
 }
@@ -509,6 +541,7 @@ extern "C" const uint32_t* ws_plan_lake_counts(const ws_plan* p) { return p ? p-
 static ws_status plan_rep_table(ws_plan* p, uint32_t level) {
   ws_ctx* ctx = p->ctx;
   if (!p->merged) return fail(ctx, WS_ERR_INVALID_ARG, "merging snapshot requested but the last run was not WS_MERGING");
+  if (!p->tree_built) WS_TRY(plan_build_tree(p));
   if (p->nseeds > p->rep_cap || !p->rep) {
     cudaFree(p->rep);
     p->rep = nullptr; p->rep_cap = 0; p->rep_level = -1;
@@ -697,8 +730,8 @@ extern "C" ws_status ws_plan_strip_edges(ws_plan* p, const void** d_ab, const vo
     p->edges_cap = cap;
   }
   // labels are GLOBAL colours here (colour_base + i + 1), so the colour id is label - 1: offsets {0, ...}
-  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, p->cfg.max_water_level, p->mb.red_ab,
-                                   p->mb.red_w, p->mb.red_count, s));
+  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, 0, p->mb.red_ab, p->mb.red_w,
+                                   p->mb.red_count, s));
   WS_CUDA(ctx, launch_count_present(p->fb.lab, p->d, p->seeds, (uint32_t)p->nseeds, p->colour_base, p->mb.ndistinct, s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.ndistinct, 4, cudaMemcpyDeviceToHost, s));
@@ -739,8 +772,9 @@ extern "C" ws_status ws_plan_union_edges(ws_plan* p, const void* d_ab, const voi
   WS_CUDA(ctx, cudaMemcpyAsync(p->mb.red_count, p->h_ctrl + FC_WORDS + 2, 4, cudaMemcpyHostToDevice, s));
   MergeBuffers m = p->mb;
   m.edges = p->union_edges;
-  WS_CUDA(ctx, launch_red_sort((const uint2*)d_ab, (const uint8_t*)d_w, m.red_count, m.level_hist, m.level_cursor,
-                               m.edges, s));
+  WS_CUDA(ctx, launch_red_sort((const uint2*)d_ab, (const uint8_t*)d_w, m.red_count, 1, p->d_strip_off, 1, m.level_hist,
+                               m.level_cursor, m.fin_hist, m.edges, s));
+  WS_CUDA(ctx, cudaMemsetAsync(m.fin_hist, 0, 256 * sizeof(uint32_t), s));  // strips emit no FINAL edges
   WS_CUDA(ctx, launch_uf_reset(m, (uint32_t)ncolours, s));
   WS_CUDA(ctx, cudaMemcpyAsync(m.ndistinct, p->h_ctrl + FC_WORDS + 3, 4, cudaMemcpyHostToDevice, s));
   WS_CUDA(ctx, launch_union_levels(m, p->d_strip_off, 1, max_water_level, ctx->union_grid, s));

@@ -436,13 +436,13 @@ cudaError_t launch_union_levels(MergeBuffers m, const uint32_t* seed_off, int n_
   return cudaLaunchCooperativeKernel((const void*)union_levels_kernel, dim3(grid), dim3(256), args, 0, s);
 }
 
-// counts[img][l] = colours present - unions at levels <= l
+// counts[img][l] = colours present - forest edges at levels <= l (unions of the global pass + FINAL edges)
 __global__ void lake_counts_kernel(MergeBuffers m, int n_img, uint32_t lmax) {
   const int img = blockIdx.x * blockDim.x + threadIdx.x;
   if (img >= n_img) return;
   uint32_t n = m.ndistinct[img];
   for (uint32_t l = 0; l < 256; ++l) {
-    if (l <= lmax) n -= m.unions[(size_t)img * 256 + l];
+    if (l <= lmax) n -= m.unions[(size_t)img * 256 + l] + m.fin_hist[(size_t)img * 256 + l];
     m.counts[(size_t)img * 256 + l] = (l <= lmax) ? n : 0u;
   }
 }

@@ -96,16 +96,20 @@ struct MergeBuffers {
   uint32_t* hook_to;      // [nseeds] immutable link written once when a root is hooked
   uint8_t* hook_lvl;      // [nseeds] level of that link, 255 = still a root
   uint32_t* unions;       // [n_img][256] successful unions per level
+  uint32_t* fin_hist;     // [n_img][256] FINAL forest edges per level (contracted in their tile, never unioned globally)
   uint32_t* ndistinct;    // [n_img] colours present on the canvas
   uint32_t* counts;       // [n_img][256] lakes per level
 };
-// per-tile exact Kruskal in shared memory: emits only the tile's spanning-forest edges (merge.cu)
+// per-tile contraction + spanning-forest reduction in shared memory (merge.cu).  Edges: .x / .y = global
+// colour ids, bit 31 of .y = FINAL (a certain forest edge, only to be counted).  contract = 0: no FINAL edges.
 size_t merge_reduce_capacity(const ImageDims& d);
 cudaError_t launch_merge_reduce(const uint32_t* lab, const uint8_t* lvl, ImageDims d, const uint32_t* seed_off,
-                                uint32_t lmax, uint2* red_ab, uint8_t* red_w, uint32_t* red_count, cudaStream_t s);
-// counting sort of the reduced edges by level: level_hist[0..256] = exclusive offsets, edges = buckets
-cudaError_t launch_red_sort(const uint2* red_ab, const uint8_t* red_w, const uint32_t* red_count,
-                            uint32_t* level_hist, uint32_t* level_cursor, uint2* edges, cudaStream_t s);
+                                int contract, uint2* red_ab, uint8_t* red_w, uint32_t* red_count, cudaStream_t s);
+// counting sort by level: level_hist[0..256] = exclusive offsets, edges = buckets.  all = 0: only DEFERRED
+// edges are bucketed, FINAL ones are counted into fin_hist[slice][level]; all = 1: every edge is bucketed.
+cudaError_t launch_red_sort(const uint2* red_ab, const uint8_t* red_w, const uint32_t* red_count, int all,
+                            const uint32_t* seed_off, int n_img, uint32_t* level_hist, uint32_t* level_cursor,
+                            uint32_t* fin_hist, uint2* edges, cudaStream_t s);
 cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,
                            const uint32_t* seed_off, uint32_t nseeds, cudaStream_t s);
 cudaError_t launch_uf_reset(MergeBuffers m, uint32_t n, cudaStream_t s);
