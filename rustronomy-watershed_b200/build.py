@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libws_b200.so")
-SOURCES = ["kernels.cu", "flood.cu", "merge.cu", "engine.cu"]
+SOURCES = ["kernels.cu", "flood.cu", "labels.cu", "merge.cu", "engine.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "ws_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,5 +1,4 @@
-// flood.cu -- K2: arrival times of all water levels in one persistent kernel, and the
-// parent-pointer kernel that turns them into the reference's colour decision.
+// flood.cu -- K2: arrival times of all water levels in one persistent kernel.
 //
 // Replaces the reference's level loop x 'colouring_loop x find_flooded_px x write-back
 // (lib.rs:1379-1438 / 1689-1748 and 196-257).  See common.cuh for the arrival-time
@@ -676,53 +675,6 @@ cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int bu
   const int want = d.tiles_total();
   const int g = want < grid ? (want > 0 ? want : 1) : grid;
   flood_kernel<<<g, FLOOD_THREADS, 0, s>>>(a);
-  return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------
-// K3a  parent pointers + level bytes
-// ---------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256) parent_kernel(FloodBuffers b, ImageDims d) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = blockIdx.y;
-  const int img = blockIdx.z;
-  if (c >= d.cols) return;
-  const size_t p = (size_t)img * d.px_per_img() + (size_t)r * d.cols + c;
-  const uint32_t* Tq = b.T + (size_t)img * d.t_plane() + d.t_index(r, c);
-  const int tp = d.t_pitch();
-  const uint32_t t = Tq[0];
-  b.lvl[p] = (t >= T_INF) ? (uint8_t)255 : (uint8_t)(t >> 24);
-  if (t >= T_INF) {
-    b.lab[p] = LAB_RESOLVED;  // UNCOLOURED
-    return;
-  }
-  if (d.is_halo_row(r)) {
-    // a neighbouring strip owns this pixel: its label arrives by exchange; until then the word
-    // points at itself ("pending"), which pointer jumping leaves alone
-    b.lab[p] = (uint32_t)p;
-    return;
-  }
-  if (t == 0u) return;  // seed: coloured by seed_init
-  // A coloured non-seed pixel is interior, so all four neighbours exist.  The coloured
-  // neighbours the reference sees when it colours p are exactly those with T(q) < T(p);
-  // `col0` is the first of them in the order down, right, left, up (lib.rs:190, 245).
-  size_t q;
-  if (Tq[tp] < t) q = p + d.cols;
-  else if (Tq[1] < t) q = p + 1;
-  else if (Tq[-1] < t) q = p - 1;
-  else if (Tq[-tp] < t) q = p - d.cols;
-  else {
-    atomicOr(&b.ctrl[FC_ERROR], 4u);  // cannot happen at a fixed point
-    b.lab[p] = LAB_RESOLVED;
-    return;
-  }
-  b.lab[p] = (uint32_t)q;
-}
-
-cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s) {
-  dim3 grid((d.cols + 255) / 256, d.rows, d.n_img);
-  parent_kernel<<<grid, 256, 0, s>>>(b, d);
   return cudaGetLastError();
 }
 

@@ -176,73 +176,7 @@ static int coop_max_grid(const void* fn, int threads, int device) {
   return per_sm * sms;
 }
 
-// ===========================================================================
-// K3  labels: pointer jumping (the parent pointers come from flood.cu)
-// ===========================================================================
-
-// Pointer jumping to the seed: lab[p] <- lab[lab[p]] until every word is a resolved label.
-// In-place and racy on purpose: whatever a thread reads is a valid ancestor or the final label.
-// One word: follow the pointer once.  Returns the new word; sets `pending` when the result is still a
-// pointer that can move again (w == v means the chain ends at a pending halo pixel of a strip).
-__device__ __forceinline__ uint32_t jump_word(const uint32_t* lab, uint32_t v, uint32_t w, int& pending) {
-  if (v & LAB_RESOLVED) return v;
-  if (w == v) return v;
-  if (!(w & LAB_RESOLVED)) pending = 1;
-  return w;
-}
-
-__global__ void __launch_bounds__(256) jump_kernel(uint32_t* __restrict__ lab, size_t n, uint32_t* ctrl) {
-  cg::grid_group grid = cg::this_grid();
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t n4 = n / 4;
-  uint4* lab4 = reinterpret_cast<uint4*>(lab);
-  for (uint32_t round = 0;; ++round) {
-    const int cur = round % 3;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      st_cg(&ctrl[FC_JUMP_FLAG0 + (round + 1) % 3], 0u);
-      atomicAdd(&ctrl[FC_JUMP_ROUNDS], 1u);
-    }
-    int pending = 0;
-    // four words per thread: the four dependent gathers are issued together (the scalar version was
-    // bound by the latency of one load -> gather -> store chain per thread)
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      const uint4 v = __ldcg(lab4 + i);
-      if ((v.x & v.y & v.z & v.w) & LAB_RESOLVED) continue;
-      const uint32_t w0 = (v.x & LAB_RESOLVED) ? v.x : ld_cg(lab + v.x);
-      const uint32_t w1 = (v.y & LAB_RESOLVED) ? v.y : ld_cg(lab + v.y);
-      const uint32_t w2 = (v.z & LAB_RESOLVED) ? v.z : ld_cg(lab + v.z);
-      const uint32_t w3 = (v.w & LAB_RESOLVED) ? v.w : ld_cg(lab + v.w);
-      uint4 o;
-      o.x = jump_word(lab, v.x, w0, pending);
-      o.y = jump_word(lab, v.y, w1, pending);
-      o.z = jump_word(lab, v.z, w2, pending);
-      o.w = jump_word(lab, v.w, w3, pending);
-      if (o.x != v.x || o.y != v.y || o.z != v.z || o.w != v.w) __stcg(lab4 + i, o);
-    }
-    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      const uint32_t v = ld_cg(lab + i);
-      if (!(v & LAB_RESOLVED)) {
-        const uint32_t o = jump_word(lab, v, ld_cg(lab + v), pending);
-        if (o != v) st_cg(lab + i, o);
-      }
-    }
-    if (__syncthreads_or(pending) && threadIdx.x == 0) st_cg(&ctrl[FC_JUMP_FLAG0 + cur], 1u);
-    grid.sync();
-    if (ld_cg(&ctrl[FC_JUMP_FLAG0 + cur]) == 0u) break;
-  }
-}
-
-int jump_max_grid(int device) { return coop_max_grid((const void*)jump_kernel, 256, device); }
-
-cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s) {
-  size_t n = d.px_total();
-  uint32_t* lab = b.lab;
-  uint32_t* ctrl = b.ctrl;
-  void* args[] = {&lab, &n, &ctrl};
-  const size_t want = (n + 255) / 256;
-  const int g = (size_t)grid > want ? (int)(want ? want : 1) : grid;
-  return cudaLaunchCooperativeKernel((const void*)jump_kernel, dim3(g), dim3(256), args, 0, s);
-}
+// K3 (labels) lives in labels.cu.
 
 // ===========================================================================
 // K4  merging: the edge reduction lives in merge.cu; union-find over the reduced edges below
