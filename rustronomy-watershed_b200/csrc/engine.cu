@@ -275,6 +275,7 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->fb.pix, p->d.pix_plane() * n_img);
   alloc((void**)&p->fb.lab, npx * 4);
   alloc((void**)&p->fb.lvl, npx);
+  alloc((void**)&p->fb.rim, rim_words(p->d) * 4);
   p->fb.qcap = (uint32_t)ntiles + FLOOD_QSLACK;
   alloc((void**)&p->fb.qslots, (size_t)FLOOD_BUCKETS * p->fb.qcap * 4);
   alloc((void**)&p->fb.qmask, ntiles * 8);
@@ -314,6 +315,7 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->union_edges);
   cudaFree(p->fb.lab);
   cudaFree(p->fb.lvl);
+  cudaFree(p->fb.rim);
   cudaFree(p->fb.qslots);
   cudaFree(p->fb.qmask);
   cudaFree(p->fb.ctrl);
@@ -701,8 +703,8 @@ extern "C" ws_status ws_plan_strip_import_labels(ws_plan* p, const uint32_t* d_t
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  if (d_top && p->d.halo_top) WS_CUDA(ctx, launch_strip_import_lab(p->fb.lab, p->d, 0, d_top, s));
-  if (d_bottom && p->d.halo_bottom) WS_CUDA(ctx, launch_strip_import_lab(p->fb.lab, p->d, p->d.rows - 1, d_bottom, s));
+  if (d_top && p->d.halo_top) WS_CUDA(ctx, launch_strip_import_lab(p->fb, p->d, 0, d_top, s));
+  if (d_bottom && p->d.halo_bottom) WS_CUDA(ctx, launch_strip_import_lab(p->fb, p->d, p->d.rows - 1, d_bottom, s));
   WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl + FC_JUMP_FLAG0, 0, sizeof(uint32_t) * 3, s));
   WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl + FC_STRIP_PENDING, 0, sizeof(uint32_t), s));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));

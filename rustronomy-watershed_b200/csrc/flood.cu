@@ -28,51 +28,8 @@
 
 namespace ws {
 
-// ---------------------------------------------------------------------------
-// small PTX helpers (mbarrier + bulk async copy + named barriers)
-// ---------------------------------------------------------------------------
+// (mbarrier / bulk-copy helpers: common.cuh)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return done != 0u;
-}
-// global -> shared bulk copy (16-byte aligned, multiple of 16 bytes), completes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ void consumer_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(FLOOD_CONSUMERS) : "memory");
 }
@@ -717,14 +674,18 @@ __global__ void __launch_bounds__(256) strip_export_lab_kernel(const uint32_t* _
   if (rb >= 0) out_b[c] = ld_cg(lab + (size_t)rb * d.cols + c);
 }
 
-// resolved labels of the neighbour's boundary row replace the pending words of halo row `row`
-__global__ void __launch_bounds__(256) strip_import_lab_kernel(uint32_t* __restrict__ lab, ImageDims d, int row,
-                                                               const uint32_t* __restrict__ in) {
+// resolved labels of the neighbour's boundary row replace the pending words of halo row `row`, in the
+// label plane and in the row's pending slots behind the rim entries (labels.cu)
+__global__ void __launch_bounds__(256) strip_import_lab_kernel(FloodBuffers b, ImageDims d, int row,
+                                                               const uint32_t* __restrict__ in, size_t slot0) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d.cols) return;
   const uint32_t v = in[c];
-  uint32_t* l = lab + (size_t)row * d.cols + c;
-  if ((v & LAB_RESOLVED) && !(ld_cg(l) & LAB_RESOLVED)) st_cg(l, v);
+  uint32_t* l = b.lab + (size_t)row * d.cols + c;
+  if ((v & LAB_RESOLVED) && !(ld_cg(l) & LAB_RESOLVED)) {
+    st_cg(l, v);
+    st_cg(b.rim + slot0 + c, v);
+  }
 }
 
 // pixels of the owned rows [r0, r1] whose label is still a pointer
@@ -754,8 +715,9 @@ cudaError_t launch_strip_export_lab(const uint32_t* lab, ImageDims d, int ra, in
   strip_export_lab_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(lab, d, ra, rb, out_a, out_b);
   return cudaGetLastError();
 }
-cudaError_t launch_strip_import_lab(uint32_t* lab, ImageDims d, int row, const uint32_t* in, cudaStream_t s) {
-  strip_import_lab_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(lab, d, row, in);
+cudaError_t launch_strip_import_lab(FloodBuffers b, ImageDims d, int row, const uint32_t* in, cudaStream_t s) {
+  const size_t slot0 = rim_words(d) - 2 * (size_t)d.cols + (row == 0 ? 0 : (size_t)d.cols);
+  strip_import_lab_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(b, d, row, in, slot0);
   return cudaGetLastError();
 }
 cudaError_t launch_strip_count_pending(const uint32_t* lab, ImageDims d, int r0, int r1, uint32_t* ctrl,

@@ -37,6 +37,7 @@ struct FloodBuffers {
   uint8_t* pix;      // [n_img][pix_rows][pix_pitch] image bytes re-encoded for the flood (255 = never floods)
   uint32_t* lab;     // [px_total] label / parent words
   uint8_t* lvl;      // [px_total] level of colouring
+  uint32_t* rim;     // [tiles_total][188] label words of the tiles' rim pixels + [2][cols] pending halo slots (labels.cu)
   uint32_t* qslots;  // [FLOOD_BUCKETS][qcap] ring buffers of tile ids, Q_EMPTY = not written yet
   unsigned long long* qmask;  // [tiles_total] bit b: an entry for the tile sits in bucket b; bit 63: Q_DIRTY
   uint32_t* ctrl;    // [FC_WORDS]
@@ -70,7 +71,7 @@ cudaError_t launch_strip_import_T(FloodBuffers b, ImageDims d, int row, int nb_r
                                   int bucket_shift, cudaStream_t s);
 cudaError_t launch_strip_export_lab(const uint32_t* lab, ImageDims d, int ra, int rb, uint32_t* out_a,
                                     uint32_t* out_b, cudaStream_t s);
-cudaError_t launch_strip_import_lab(uint32_t* lab, ImageDims d, int row, const uint32_t* in, cudaStream_t s);
+cudaError_t launch_strip_import_lab(FloodBuffers b, ImageDims d, int row, const uint32_t* in, cudaStream_t s);
 cudaError_t launch_strip_count_pending(const uint32_t* lab, ImageDims d, int r0, int r1, uint32_t* ctrl,
                                        cudaStream_t s);
 cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseeds, size_t rows, size_t cols,
@@ -81,6 +82,7 @@ int flood_bucket_shift(size_t nseeds, const ImageDims& d);
 cudaError_t launch_unpad_T(const uint32_t* Tp, ImageDims d, uint32_t* out, cudaStream_t s);
 
 // --- labels (colour decision of lib.rs:235-255 with the `col0` tie-break) ---
+size_t rim_words(const ImageDims& d);
 cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s);
 cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s);
 

@@ -29,38 +29,44 @@ constexpr int MR_NW = TILE_W + 1;              // node grid = tile pixels + righ
 constexpr int MR_NH = TILE_H + 1;
 constexpr int MR_NODES = MR_NW * MR_NH;        // 2145
 constexpr int MR_THREADS = 256;
+constexpr int MR_WARPS = MR_THREADS / 32;
 constexpr int MR_PER_THREAD = (MR_NODES + MR_THREADS - 1) / MR_THREADS;  // 9
 constexpr int MR_HASH = 4096;                  // label -> dense id table (load factor <= 0.53)
+constexpr int MR_SEG = 2 * 32 * ROWS_PER_THREAD;  // 512 edge slots per warp: 32 lanes x 8 pixels x (right, down)
 constexpr uint32_t MR_NONE = 0xFFFFFFFFu;
 constexpr uint16_t MR_NOLAB = 0xFFFFu;
+static_assert(MR_WARPS * MR_SEG == MR_HASH, "the edge list reuses the id table's memory");
 
+// Shared memory of one tile, 48.6 KB (4 CTAs per SM).  An edge is one word: id(a) | id(b) << 12 | level << 24.
 struct MergeSmem {
-  uint16_t lid[MR_NODES];        // node -> dense id of its basin in this tile (MR_NOLAB: uncoloured)
-  uint8_t lvl[MR_NODES + 3];
   uint32_t label_of[MR_NODES];   // dense id -> colour
   uint16_t parent[MR_NODES];     // union-find over dense ids; only a root's own thread re-parents it
-  uint16_t comp[MR_NODES];       // root of every id at the start of the round
-  uint16_t rep[MR_NODES];        // root after the contraction stage (the component's open basin)
-  uint8_t open[MR_NODES];        // dense id: the basin has pixels on the tile's rim
+  uint8_t flags[MR_NODES + 3];   // dense id, bit 0: the basin has pixels on the tile's rim (open),
+                                 //           bit 1: it went under another component in the contraction stage
   union {
-    uint32_t table[MR_HASH];       // while dense ids are handed out: 0 = free, else id + 1 (open addressing)
+    uint32_t table[MR_HASH];     // while dense ids are handed out: 0 = free, else the label / the id
+    uint32_t edge[MR_HASH];      // afterwards: 8 warp-private segments of live edges, compacted every round
+  } a;
+  union {
+    struct { uint16_t lid[MR_NODES]; uint8_t lvl[MR_NODES + 3]; } n;  // until the edge list is built
     struct {
-      uint32_t best[MR_NODES];     // per root: smallest (level << 16 | edge id) offered this round
-      uint16_t out_edge[MR_NODES]; // forest edges found (bit 15: FINAL) ...
-      uint8_t out_lvl[MR_NODES];   // ... and their levels
+      uint32_t best[MR_NODES];   // root: smallest (level << 16 | slot) offered this round; after the id went
+                                 // under another component: the edge it went along (an edge word)
+      uint16_t comp[MR_NODES];   // root of every id at the start of the round | open << 15
+      uint16_t rep[MR_NODES];    // root after the contraction stage (the component's open basin)
     } r;
-  } u;
+  } b;
   uint32_t nlab, nout, gpos, first;
 };
 
-// `contract` = 0 (row strips: a strip's rim is not only its tiles' rims) skips stage 1.
+// `contract` = 0 (row strips: a strip's rim is not only its tiles' rims) skips stage 0.
 __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t* __restrict__ lab,
                                                                   const uint8_t* __restrict__ lvl, ImageDims d,
                                                                   const uint32_t* __restrict__ seed_off, int contract,
                                                                   uint2* __restrict__ red_ab, uint8_t* __restrict__ red_w,
                                                                   uint32_t* __restrict__ red_count) {
   __shared__ MergeSmem sm;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tpi = d.tiles_per_img();
   const int img = blockIdx.x / tpi;
   const int trem = blockIdx.x - img * tpi;
@@ -85,13 +91,13 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
         L[k] = lab[p] & LAB_MASK;
         v = lvl[p];
       }
-      sm.lvl[i] = (uint8_t)v;
-      sm.open[i] = 0;
+      sm.b.n.lvl[i] = (uint8_t)v;
+      sm.flags[i] = 0;
       sm.parent[i] = (uint16_t)i;
       if (L[k] != 0u && sm.first == 0u) sm.first = L[k];  // any coloured label (benign race)
     }
   }
-  for (int i = tid; i < MR_HASH; i += MR_THREADS) sm.u.table[i] = 0u;
+  for (int i = tid; i < MR_HASH; i += MR_THREADS) sm.a.table[i] = 0u;
   __syncthreads();
   {  // a tile inside one basin (most tiles of a smooth field) has no edge at all
     const uint32_t f = sm.first;
@@ -110,8 +116,8 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     uint32_t h = (l * 2654435761u) >> 20;
     if (l != 0u) {
       for (;;) {
-        uint32_t cur = ((volatile uint32_t*)sm.u.table)[h];
-        if (cur == 0u) cur = atomicCAS(&sm.u.table[h], 0u, l);
+        uint32_t cur = ((volatile uint32_t*)sm.a.table)[h];
+        if (cur == 0u) cur = atomicCAS(&sm.a.table[h], 0u, l);
         if (cur == 0u || cur == l) break;
         h = (h + 1u) & (MR_HASH - 1);
       }
@@ -122,13 +128,13 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
   {
     uint32_t key[MR_HASH / MR_THREADS];
 #pragma unroll
-    for (int k = 0; k < MR_HASH / MR_THREADS; ++k) key[k] = sm.u.table[tid + k * MR_THREADS];
+    for (int k = 0; k < MR_HASH / MR_THREADS; ++k) key[k] = sm.a.table[tid + k * MR_THREADS];
 #pragma unroll
     for (int k = 0; k < MR_HASH / MR_THREADS; ++k) {
       if (key[k] == 0u) continue;
       const uint32_t id = atomicAdd(&sm.nlab, 1u);
       sm.label_of[id] = key[k];
-      sm.u.table[tid + k * MR_THREADS] = id;  // (only this thread touches the slot in this phase)
+      sm.a.table[tid + k * MR_THREADS] = id;  // (only this thread touches the slot in this phase)
     }
   }
   __syncthreads();
@@ -139,142 +145,133 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     if (i >= MR_NODES) continue;
     uint32_t id = MR_NOLAB;
     if (L[k] != 0u) {
-      id = sm.u.table[slot[k]];
+      id = sm.a.table[slot[k]];
       const int r = i / MR_NW, c = i - r * MR_NW;
       // rim: pixels whose up / left neighbour lies outside the tile, and the neighbour row / column itself
-      if (!contract || r == TILE_H || c == TILE_W || (r == 0 && r0 > 0) || (c == 0 && c0 > 0)) sm.open[id] = 1;
+      if (!contract || r == TILE_H || c == TILE_W || (r == 0 && r0 > 0) || (c == 0 && c0 > 0)) sm.flags[id] = 1;
     }
-    sm.lid[i] = (uint16_t)id;
+    sm.b.n.lid[i] = (uint16_t)id;
   }
-  __syncthreads();  // last use of the table; u.r may be written from here on
+  __syncthreads();  // last use of the table: its memory becomes the edge list
 
-  // (c) candidate edges of my 8 pixels: endpoints as dense ids in registers, levels (0xFF = no edge)
+  // (c) the edges of my 8 pixels, compacted into my warp's segment of the edge list
   const int lc = tid % TILE_W, g = tid / TILE_W;
-  uint32_t ew[ROWS_PER_THREAD];   // level of the right edge | level of the down edge << 8
-  uint32_t ea[ROWS_PER_THREAD];   // my pixel's id | the right neighbour's id << 16
-  uint16_t ed[ROWS_PER_THREAD];   // the lower neighbour's id
-  bool have = false;
+  uint32_t* seg = sm.a.edge + warp * MR_SEG;
+  uint32_t cnt = 0;  // live edges in the segment (uniform across the warp)
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     const int r = g * ROWS_PER_THREAD + i;
     const int n = r * MR_NW + lc;
     const int gr = r0 + r, gc = c0 + lc;
-    const uint32_t a = sm.lid[n];
-    const uint32_t br = sm.lid[n + 1], bd = sm.lid[n + MR_NW];
-    uint32_t wr = 0xFFu, wd = 0xFFu;
+    const uint32_t a = sm.b.n.lid[n];
+    const uint32_t br = sm.b.n.lid[n + 1], bd = sm.b.n.lid[n + MR_NW];
+    uint32_t er = MR_NONE, ed = MR_NONE;
     // An edge belongs to the strip that owns its upper / left pixel; a halo row's own edges are the
     // neighbouring strip's.  Plain plans own every row.
     if (a != MR_NOLAB && gr < d.rows && !(d.halo_top && gr == 0) && !(d.halo_bottom && gr == d.rows - 1)) {
       const bool pin = d.is_centre(gr, gc);
       if (br != MR_NOLAB && br != a && (pin || d.is_centre(gr, gc + 1)))
-        wr = max((uint32_t)sm.lvl[n], (uint32_t)sm.lvl[n + 1]);
+        er = a | (br << 12) | (max((uint32_t)sm.b.n.lvl[n], (uint32_t)sm.b.n.lvl[n + 1]) << 24);
       if (bd != MR_NOLAB && bd != a && (pin || d.is_centre(gr + 1, gc)))
-        wd = max((uint32_t)sm.lvl[n], (uint32_t)sm.lvl[n + MR_NW]);
+        ed = a | (bd << 12) | (max((uint32_t)sm.b.n.lvl[n], (uint32_t)sm.b.n.lvl[n + MR_NW]) << 24);
     }
-    ew[i] = wr | (wd << 8);
-    ea[i] = a | (br << 16);
-    ed[i] = (uint16_t)bd;
-    have |= (ew[i] != 0xFFFFu);
+    // (no write of this loop can hit the table's last readers: they are behind the barrier above)
+    uint32_t m = __ballot_sync(0xffffffffu, er != MR_NONE);
+    if (er != MR_NONE) seg[cnt + __popc(m & ((1u << lane) - 1u))] = er;
+    cnt += __popc(m);
+    m = __ballot_sync(0xffffffffu, ed != MR_NONE);
+    if (ed != MR_NONE) seg[cnt + __popc(m & ((1u << lane) - 1u))] = ed;
+    cnt += __popc(m);
   }
-  if (!__syncthreads_or(have)) return;  // no edge between different basins in this tile
+  if (!__syncthreads_or(cnt != 0u)) return;  // no edge between different basins in this tile
+  // (lid / lvl are dead from here on: their memory becomes best / comp / rep)
+  for (int i = tid; i < nlab; i += MR_THREADS) {
+    sm.b.r.best[i] = MR_NONE;
+    sm.b.r.comp[i] = (uint16_t)i;
+    sm.b.r.rep[i] = (uint16_t)i;
+  }
+  __syncthreads();
 
   // (d) stage 0: contraction (only components of closed basins pick), stage 1: spanning forest of the rest.
-  // Keys (level << 16 | edge id) are distinct, so the picks of a round form a forest apart from mutual
-  // picks of one edge, where the larger root goes under the smaller.  comp[] = root | open << 15.
+  // Keys (level << 16 | slot in the edge list) are distinct within a round, so the picks of a round form
+  // a forest apart from mutual picks of one edge, where the larger root goes under the smaller.  (The
+  // order among equal levels may differ from round to round: every round is a valid Boruvka step on the
+  // graph contracted so far.)
   constexpr uint32_t OPEN = 0x8000u, ROOT = 0x7FFFu;
-  // Per thread: bit 2i / 2i+1 of `live` = right / down edge of pixel i still has to be looked at in this
-  // stage; `asleep` = edges between two open components, which only stage 1 can use.
-  uint32_t live = 0, asleep = 0;
-#pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    if ((ew[i] & 0xFFu) != 0xFFu) live |= 1u << (2 * i);
-    if ((ew[i] >> 8) != 0xFFu) live |= 2u << (2 * i);
-  }
   for (int stage = contract ? 0 : 1; stage < 2; ++stage) {
     const uint32_t picks = stage == 1 ? OPEN : 0u;  // a component picks when (comp & OPEN) <= picks
-    if (stage == 1) live |= asleep;
     for (;;) {
-#ifdef WS_MERGE_STATS
-      if (tid == 0) atomicAdd(&red_count[4 + stage], 1u);
-      atomicAdd(&red_count[6 + stage], (uint32_t)__popc(live));
-#endif
-      // roots (chains are short; reads racing with the flattening stores still see an ancestor)
+      // roots (reads racing with the flattening stores still see an ancestor).  An id that was a root
+      // and went under another component in the previous round keeps the edge it went along.
       for (int i = tid; i < nlab; i += MR_THREADS) {
         uint32_t x = (uint32_t)i;
         for (uint32_t p = sm.parent[x]; p != x; p = sm.parent[x]) x = p;
-        sm.parent[i] = (uint16_t)x;
-        sm.comp[i] = (uint16_t)(x | (sm.open[x] ? OPEN : 0u));
-        sm.u.r.best[i] = MR_NONE;
-      }
-      __syncthreads();
-      bool any = false;
-      if (live) {
-        uint32_t still = 0;
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          if (!(live & (3u << (2 * i)))) continue;
-          const uint32_t n = (g * ROWS_PER_THREAD + i) * MR_NW + lc;
-          const uint32_t cu = sm.comp[ea[i] & 0xFFFFu];
-          const bool pu = (cu & OPEN) <= picks;
-          if (live & (1u << (2 * i))) {  // right edge
-            const uint32_t cv = sm.comp[ea[i] >> 16];
-            if (cu != cv) {
-              const bool pv = (cv & OPEN) <= picks;
-              if (pu | pv) {
-                const uint32_t key = ((ew[i] & 0xFFu) << 16) | (n * 2u);
-                if (pu) atomicMin(&sm.u.r.best[cu & ROOT], key);
-                if (pv) atomicMin(&sm.u.r.best[cv & ROOT], key);
-                any = true;
-                still |= 1u << (2 * i);
-              } else {
-                asleep |= 1u << (2 * i);  // between two open components: nothing to do before stage 1
-              }
-            }  // else: both ends already in one component -- dead for good
-          }
-          if (live & (2u << (2 * i))) {  // down edge
-            const uint32_t cv = sm.comp[ed[i]];
-            if (cu != cv) {
-              const bool pv = (cv & OPEN) <= picks;
-              if (pu | pv) {
-                const uint32_t key = ((ew[i] >> 8) << 16) | (n * 2u + 1u);
-                if (pu) atomicMin(&sm.u.r.best[cu & ROOT], key);
-                if (pv) atomicMin(&sm.u.r.best[cv & ROOT], key);
-                any = true;
-                still |= 2u << (2 * i);
-              } else {
-                asleep |= 2u << (2 * i);
-              }
-            }
+        if ((sm.b.r.comp[i] & ROOT) == (uint32_t)i) {
+          if (x != (uint32_t)i) {
+            sm.b.r.best[i] = sm.a.edge[sm.b.r.best[i] & 0xFFFFu];
+            if (stage == 0) sm.flags[i] |= 2;
+          } else {
+            sm.b.r.best[i] = MR_NONE;
           }
         }
-        live = still;
+        sm.parent[i] = (uint16_t)x;
+        sm.b.r.comp[i] = (uint16_t)(x | ((sm.flags[x] & 1) ? OPEN : 0u));
       }
+      __syncthreads();
+      // one pass over my warp's live edges: drop those inside one component, keep the rest compacted,
+      // offer each to the components at its ends
+      bool any = false;
+      uint32_t kept = 0;
+      for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        uint32_t e = 0, cu = 0, cv = 0;
+        if (j < cnt) {
+          e = seg[j];
+          cu = sm.b.r.comp[e & 0xFFFu];
+          cv = sm.b.r.comp[(e >> 12) & 0xFFFu];
+        }
+        const bool alive = cu != cv;
+        const uint32_t m = __ballot_sync(0xffffffffu, alive);  // (also orders this step's reads before its writes)
+        if (alive) {
+          const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
+          seg[pos] = e;
+          const uint32_t key = ((e >> 24) << 16) | (uint32_t)(warp * MR_SEG + pos);
+          const bool pu = (cu & OPEN) <= picks, pv = (cv & OPEN) <= picks;
+          if (pu) atomicMin(&sm.b.r.best[cu & ROOT], key);
+          if (pv) atomicMin(&sm.b.r.best[cv & ROOT], key);
+          any |= pu | pv;
+        }
+        kept += __popc(m);
+      }
+      cnt = kept;
       if (!__syncthreads_or(any)) break;
       // every picking root goes under the component at the other end of its edge
       for (int i = tid; i < nlab; i += MR_THREADS) {
-        const uint32_t key = sm.u.r.best[i];
-        if (key == MR_NONE) continue;  // (only roots ever receive offers)
-        const uint32_t e = key & 0xFFFFu;
-        const uint32_t n = e >> 1;
-        const uint32_t q = n + ((e & 1u) ? MR_NW : 1);
-        const uint32_t cu = sm.comp[sm.lid[n]] & ROOT, cv = sm.comp[sm.lid[q]] & ROOT;
+        if ((sm.b.r.comp[i] & ROOT) != (uint32_t)i) continue;
+        const uint32_t key = sm.b.r.best[i];
+        if (key == MR_NONE) continue;
+        const uint32_t e = sm.a.edge[key & 0xFFFFu];
+        const uint32_t cu = sm.b.r.comp[e & 0xFFFu] & ROOT, cv = sm.b.r.comp[(e >> 12) & 0xFFFu] & ROOT;
         const uint32_t other = cu == (uint32_t)i ? cv : cu;
-        if (sm.u.r.best[other] == key && (uint32_t)i < other) continue;  // mutual pick: the other one moves
+        if (sm.b.r.best[other] == key && (uint32_t)i < other) continue;  // mutual pick: the other one moves
         sm.parent[i] = (uint16_t)other;
-        const uint32_t o = atomicAdd(&sm.nout, 1u);
-        sm.u.r.out_edge[o] = (uint16_t)(e | (stage == 0 ? 0x8000u : 0u));
-        sm.u.r.out_lvl[o] = (uint8_t)(key >> 16);
       }
       __syncthreads();
     }
     if (stage == 0) {  // comp[] is current (no hook since the last flatten): the contracted components
-      for (int i = tid; i < nlab; i += MR_THREADS) sm.rep[i] = sm.comp[i] & ROOT;
+      for (int i = tid; i < nlab; i += MR_THREADS) sm.b.r.rep[i] = sm.b.r.comp[i] & ROOT;
       __syncthreads();
     }
   }
 
-  // (e) append the edges to the global list as global colour ids: FINAL edges (bit 31 of .y) between the
-  // two basins themselves, DEFERRED ones between the open basins of the contracted components
+  // (e) every id that is not a root went under another component along exactly one edge: append those
+  // edges to the global list as global colour ids -- FINAL edges (bit 31 of .y) between the two basins
+  // themselves, DEFERRED ones between the open basins of the contracted components
+  uint32_t mine = 0;
+  if (tid == 0) sm.first = 0;  // from here on: cursor into this tile's part of the global list
+  for (int i = tid; i < nlab; i += MR_THREADS) mine += (sm.parent[i] != (uint16_t)i);
+  if (mine) atomicAdd(&sm.nout, mine);
+  __syncthreads();
   const uint32_t nout = sm.nout;
 #ifdef WS_MERGE_STATS
   if (tid == 0) { atomicAdd(&red_count[8], 1u); atomicAdd(&red_count[9], (uint32_t)nlab); atomicAdd(&red_count[10], nout); }
@@ -282,17 +279,17 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
   if (nout == 0u) return;
   if (tid == 0) sm.gpos = atomicAdd(red_count, nout);
   __syncthreads();
-  const uint32_t gpos = sm.gpos;
   const uint32_t gbase = __ldg(seed_off + img) - 1u;  // global colour id = seed_off[img] + colour - 1
-  for (uint32_t k = tid; k < nout; k += MR_THREADS) {
-    const uint32_t oe = sm.u.r.out_edge[k];
-    const uint32_t e = oe & 0x7FFFu, fin = oe >> 15;
-    const uint32_t n = e >> 1;
-    const uint32_t q = n + ((e & 1u) ? MR_NW : 1);
-    uint32_t ia = sm.lid[n], ib = sm.lid[q];
-    if (!fin && contract) { ia = sm.rep[ia]; ib = sm.rep[ib]; }
-    red_ab[gpos + k] = make_uint2(gbase + sm.label_of[ia], (gbase + sm.label_of[ib]) | (fin << 31));
-    red_w[gpos + k] = sm.u.r.out_lvl[k];
+  uint32_t at = mine ? sm.gpos + atomicAdd(&sm.first, mine) : 0u;
+  for (int i = tid; i < nlab; i += MR_THREADS) {
+    if (sm.parent[i] == (uint16_t)i) continue;
+    const uint32_t e = sm.b.r.best[i];
+    const uint32_t fin = (sm.flags[i] >> 1) & 1u;
+    uint32_t ia = e & 0xFFFu, ib = (e >> 12) & 0xFFFu;
+    if (!fin && contract) { ia = sm.b.r.rep[ia]; ib = sm.b.r.rep[ib]; }
+    red_ab[at] = make_uint2(gbase + sm.label_of[ia], (gbase + sm.label_of[ib]) | (fin << 31));
+    red_w[at] = (uint8_t)(e >> 24);
+    ++at;
   }
 }
 
