@@ -242,7 +242,8 @@ ws_status ws_plan_snapshot(ws_plan *plan, ws_kind kind, size_t i, uint8_t level,
                            uint64_t *d_out);
 /* Counters of the last run: [0] stale worklist entries dropped, [1] tile activations,
  * [2] pointer-jumping rounds, [3] merge edges, [4] kernels launched,
- * [5] in-tile iteration phases of the flood.                                  */
+ * [5] in-tile iteration phases of the flood, [6] / [7] kilo-cycles the flood's consumer
+ * warps spent waiting for a staged tile / iterating, summed over the CTAs.     */
 ws_status ws_plan_stats(ws_plan *plan, uint64_t out[8]);
 
 /* ---- one large field as row strips over several plans / GPUs --------------

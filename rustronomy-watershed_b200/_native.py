@@ -319,4 +319,5 @@ class Plan:
         arr = (C.c_uint64 * 8)()
         self.ctx.check(self.lib.ws_plan_stats(self.handle, C.byref(arr)))
         return {"stale_entries": arr[0], "tile_activations": arr[1], "jump_rounds": arr[2],
-                "merge_edges": arr[3], "kernel_launches": arr[4], "flood_phases": arr[5]}
+                "merge_edges": arr[3], "kernel_launches": arr[4], "flood_phases": arr[5],
+                "flood_wait_kcycles": arr[6], "flood_busy_kcycles": arr[7]}

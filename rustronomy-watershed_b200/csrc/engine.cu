@@ -56,6 +56,7 @@ struct ws_plan {
   uint32_t* d_strip_off = nullptr;   // [2] seed offsets {0, nseeds} of a strip run
   uint32_t colour_base = 0;          // strips: colour of local seed i = colour_base + i + 1
   int bucket_shift = 2;              // priority granularity of the flood's worklist in the last run
+  alignas(64) unsigned char tmaps[FLOOD_TENSOR_MAP_BYTES];  // tensor maps of fb.T / fb.pix for the flood's tile copies
   uint2* union_edges = nullptr;      // ws_plan_union_edges: the gathered edges bucketed by level
   size_t union_edges_cap = 0;
   uint32_t* chunk_counts = nullptr;  // minima scratch
@@ -292,6 +293,7 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->chunk_counts, minima_num_chunks(p->d) * 4);
   alloc((void**)&p->d_total, 16);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_ctrl, (FC_WORDS + 4) * 4);
+  if (e == cudaSuccess) e = flood_make_tensor_maps(p->fb, p->d, p->tmaps);
   for (auto& ev : p->ev)
     if (e == cudaSuccess) e = cudaEventCreate(&ev);
   if (e != cudaSuccess) {
@@ -457,7 +459,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, 0u, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[1], s));
   p->bucket_shift = flood_bucket_shift(nseeds_total, p->d);
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, s));
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
   WS_CUDA(ctx, launch_parent(p->fb, p->d, s));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
@@ -475,6 +477,8 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   p->stats[1] = p->h_ctrl[FC_ACTIVATIONS];
   p->stats[2] = p->h_ctrl[FC_JUMP_ROUNDS];
   p->stats[5] = p->h_ctrl[FC_PHASES];
+  p->stats[6] = p->h_ctrl[FC_WAIT_KCYC];
+  p->stats[7] = p->h_ctrl[FC_BUSY_KCYC];
   const uint32_t err = p->h_ctrl[FC_ERROR];
   if (err & 1u) return fail(ctx, WS_ERR_SEED_OOB, "a seed lies outside the image");
   if (err & 2u) return fail(ctx, WS_ERR_HOP_OVERFLOW, ws_status_str(WS_ERR_HOP_OVERFLOW));
@@ -639,7 +643,7 @@ extern "C" ws_status ws_plan_strip_begin(ws_plan* p, const ws_config* cfg, const
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_img, cfg->max_water_level, s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, p->d_strip_off, (uint32_t)nseeds, st->colour_base, s));
   p->bucket_shift = flood_bucket_shift(nseeds, p->d);
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, s));
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   p->stats[4] += 3;
   return check_flood_errors(p);
 }
@@ -668,7 +672,7 @@ extern "C" ws_status ws_plan_strip_import_times(ws_plan* p, const uint32_t* d_to
   if (d_bottom && p->d.halo_bottom)
     WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, p->d.rows - 1, p->d.rows - 2, d_bottom, p->bucket_shift, s));
   const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, s));  // returns at once if nothing woke up
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));  // returns at once if nothing woke up
   p->stats[4] += 3;
   WS_TRY(check_flood_errors(p));
   *changed = p->h_ctrl[FC_STRIP_CHANGED] ? 1 : 0;

@@ -22,6 +22,10 @@
 //     times must never go up.
 #include "kernels.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime, no libcuda link)
+
+#include <cstring>
+
 #ifndef WS_FLOOD_BULK
 #define WS_FLOOD_BULK 3
 #endif
@@ -221,28 +225,44 @@ cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseed
 // ---------------------------------------------------------------------------
 
 struct FloodArgs {
+  alignas(64) CUtensorMap tmT;  // arrival times: [n_img * t_rows][t_pitch] u32, box 72 x 34
+  alignas(64) CUtensorMap tmP;  // image bytes:   [n_img * pix_rows][pix_pitch] u8, box 64 x 32
   FloodBuffers b;
   ImageDims d;
   int check_overflow;
   int bucket_shift;  // worklist bucket = wake-up level >> bucket_shift
 };
 
+// one instruction per box: 2D tiled tensor copy global -> shared, completes on `bar`
+__device__ __forceinline__ void tensor_g2s(void* dst, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
 enum { DIR_UP = 0, DIR_DOWN = 1, DIR_LEFT = 2, DIR_RIGHT = 3 };
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
 
-struct FloodStage {
-  uint32_t T[STG_H * STG_W];      // staged arrival times (also the "before" image of the tile)
-  uint8_t pix[TILE_H * TILE_W];   // staged image bytes
+// Stages of the producer -> consumer ring.  (Measured: a third stage does not shorten the consumers'
+// waits -- they wait on the producer's throughput, not on its latency -- and holding more claimed tiles
+// per CTA costs re-activations on smooth fields.)
+constexpr int FLOOD_STAGES = 2;
+
+struct FloodStage {  // (tensor copies want 128-byte aligned destinations)
+  alignas(128) uint32_t T[STG_H * STG_W];      // staged arrival times (also the "before" image of the tile)
+  alignas(128) uint8_t pix[TILE_H * TILE_W];   // staged image bytes
 };
 
 struct __align__(128) FloodSmem {
-  FloodStage st[2];
+  FloodStage st[FLOOD_STAGES];
   uint32_t W[SM_H * SM_W];          // working tile incl. halo
   uint8_t wpix[TILE_H * PIX_W];     // working image tile
-  uint64_t full[2], empty[2];       // mbarriers of the ring
-  uint32_t tile[2];
-  uint32_t key[2][4];               // per stage and direction: smallest value a changed edge pixel offers
+  uint64_t full[FLOOD_STAGES], empty[FLOOD_STAGES];  // mbarriers of the ring
+  uint32_t tile[FLOOD_STAGES];
+  uint32_t key[FLOOD_STAGES][4];               // per stage and direction: smallest value a changed edge pixel offers
                                     // the pixel facing it (KEY_NONE: that neighbour need not re-run)
 };
 
@@ -448,31 +468,30 @@ __device__ __forceinline__ int flood_pop(const FloodBuffers& b, int lane, uint32
 }
 
 // Persistent kernel, no grid barrier.  See the head of this file.
-__global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(FloodArgs a) {
+__global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_constant__ FloodArgs a) {
   __shared__ FloodSmem sm;
   const ImageDims& d = a.d;
   const bool producer = threadIdx.x >= FLOOD_CONSUMERS;
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    mbar_init(&sm.full[0], 1);
-    mbar_init(&sm.full[1], 1);
-    mbar_init(&sm.empty[0], 1);
-    mbar_init(&sm.empty[1], 1);
+    for (int i = 0; i < FLOOD_STAGES; ++i) {
+      mbar_init(&sm.full[i], 1);
+      mbar_init(&sm.empty[i], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   if (producer) {
     // =========================== producer warp ============================================
-    bool pending[2] = {false, false};
-    uint32_t uses[2] = {0u, 0u};  // tiles staged into each stage so far
+    bool pending[FLOOD_STAGES];
+    uint32_t uses[FLOOD_STAGES];  // tiles staged into each stage so far
+    for (int i = 0; i < FLOOD_STAGES; ++i) { pending[i] = false; uses[i] = 0u; }
     uint32_t q_tile = TILE_NONE;  // lane j: j-th tile of the last claim
     int q_n = 0, q_i = 0;         // tiles claimed / already handed to a stage
-    // Publish the neighbours of the tile that used stage s; its consumers have released the stage.
-    auto retire = [&](int s) {
-      const uint32_t tile = sm.tile[s];
-      const uint32_t k = lane < 4 ? sm.key[s][lane] : KEY_NONE;
+    // Publish the neighbours of a finished tile (k: lanes 0..3 hold the offers per direction).
+    auto retire = [&](uint32_t tile, uint32_t k) {
       const uint32_t km = __ballot_sync(0xffffffffu, k != KEY_NONE);
       if (km) {
         const int trem = tile % d.tiles_per_img();
@@ -497,32 +516,54 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(FloodArgs a) {
       } else {
         if (lane == 0) atomicSub(&a.b.ctrl[FC_OUTSTANDING], 1u);
       }
+    };
+    auto retire_stage = [&](int s) {
+      retire(sm.tile[s], lane < 4 ? sm.key[s][lane] : KEY_NONE);
       pending[s] = false;
     };
     for (uint32_t slot = 0;; ++slot) {
-      const int s = slot & 1;
-      if (pending[s]) {  // the stage is reused: wait for its consumers, publish its tile
+      const int s = (int)(slot % FLOOD_STAGES);
+      // The stage is reused: wait for its consumers.  Its tile is published AFTER the next tile's loads
+      // have been issued (when one is already claimed), so the stage refills while we talk to the worklist.
+      bool saved = false;
+      uint32_t saved_tile = TILE_NONE, saved_k = KEY_NONE;
+      if (pending[s]) {
         mbar_wait(&sm.empty[s], (uses[s] - 1u) & 1u);
-        retire(s);
+        saved_tile = sm.tile[s];
+        saved_k = lane < 4 ? sm.key[s][lane] : KEY_NONE;
+        saved = true;
+        pending[s] = false;
       }
       // claim a tile; while there is none, finish the other stage (its pushes may be the next work)
       uint32_t tile = TILE_NONE;
       uint32_t idle = 0;
       for (;;) {
-        if (q_i == q_n) {
-          q_n = flood_pop(a.b, lane, q_tile);
-          q_i = 0;
-        }
         if (q_i < q_n) {
           tile = __shfl_sync(0xffffffffu, q_tile, q_i);
           ++q_i;
           break;
         }
-        if (pending[s ^ 1]) {
-          if (mbar_test(&sm.empty[s ^ 1], (uses[s ^ 1] - 1u) & 1u)) {
-            retire(s ^ 1);
-            continue;
+        if (saved) {  // before asking the worklist: what we publish may be exactly what we get
+          retire(saved_tile, saved_k);
+          saved = false;
+        }
+        q_n = flood_pop(a.b, lane, q_tile);
+        q_i = 0;
+        if (q_n) continue;
+        bool busy = false, retired = false;
+        for (int k = 1; k < FLOOD_STAGES && !retired; ++k) {  // the other stages, oldest first
+          const int o = (s + k) % FLOOD_STAGES;
+          if (!pending[o]) continue;
+          if (mbar_test(&sm.empty[o], (uses[o] - 1u) & 1u)) {
+            retire_stage(o);
+            retired = true;
+          } else {
+            busy = true;
           }
+        }
+        if (retired) continue;
+        if (busy) {
+          // our own consumers are still iterating
         } else if (ld_poll(&a.b.ctrl[FC_OUTSTANDING]) == 0u || (ld_poll(&a.b.ctrl[FC_ERROR]) & 24u)) {
           break;  // nothing queued, nothing in flight anywhere: the fixed point is reached
         }
@@ -551,7 +592,8 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(FloodArgs a) {
         // box rows r0-1 .. r0+32 (padded row index r0 .. r0+33), columns c0-4 .. c0+67 (padded c0 .. c0+71)
         const uint32_t* tsrc = a.b.T + (size_t)img * d.t_plane() + (size_t)(ty * TILE_H) * d.t_pitch() + tx * TILE_W;
         const uint8_t* psrc = a.b.pix + (size_t)img * d.pix_plane() + (size_t)(ty * TILE_H) * d.pix_pitch() + tx * TILE_W;
-        fence_acq_rel_gpu();  // the claim (atomic on the tile's mask word) before the loads of the tile
+        // (the claim's atomic has returned, and whoever woke the tile fenced its results before marking
+        // it: the copies below, issued after the claim, read those results from L2)
         if (!BULK_T) {
           for (int i = lane; i < STG_H * STG_W; i += 32) {
             const int r = i / STG_W, c = i - r * STG_W;
@@ -578,28 +620,41 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(FloodArgs a) {
         // on divergent halves of the warp at once, and they clobbered each other's uniform registers
         // (observed: rows landing late / in the wrong place).  One lane issues every row.
         if (lane == 0) {
-          if (BULK_T)
-            for (int r = 0; r < STG_H; ++r)
-              bulk_g2s(&sm.st[s].T[r * STG_W], tsrc + (size_t)r * d.t_pitch(), STG_W * 4, &sm.full[s]);
-          if (BULK_P)
-            for (int r = 0; r < TILE_H; ++r)
-              bulk_g2s(&sm.st[s].pix[r * TILE_W], psrc + (size_t)r * d.pix_pitch(), TILE_W, &sm.full[s]);
+          // box rows r0-1 .. r0+32 = padded rows r0 .. r0+33, columns c0-4 .. c0+67 = padded c0 .. c0+71
+          if (BULK_T) tensor_g2s(sm.st[s].T, &a.tmT, tx * TILE_W, img * d.t_rows() + ty * TILE_H, &sm.full[s]);
+          if (BULK_P) tensor_g2s(sm.st[s].pix, &a.tmP, tx * TILE_W, img * d.pix_rows() + ty * TILE_H, &sm.full[s]);
         }
         __syncwarp();
       }
       pending[s] = true;
       ++uses[s];
+      if (saved) retire(saved_tile, saved_k);
+      if (q_i == q_n && q_n > 1) {
+        // The worklist is long (the last claim took several tiles): claim ahead while the consumers are
+        // busy.  When it is short, a tile claimed early only misses what its neighbours are about to write.
+        q_n = flood_pop(a.b, lane, q_tile);
+        q_i = 0;
+      }
     }
   } else {
     // =========================== consumer warps ===========================================
+    long long waited = 0, busy = 0;  // thread 0: cycles spent waiting for a staged tile / iterating
     for (uint32_t slot = 0;; ++slot) {
-      const int s = slot & 1;
-      mbar_wait(&sm.full[s], (slot >> 1) & 1u);
+      const int s = (int)(slot % FLOOD_STAGES);
+      const long long t0 = clock64();
+      mbar_wait(&sm.full[s], (slot / FLOOD_STAGES) & 1u);
+      const long long t1 = clock64();
       const uint32_t tile = sm.tile[s];
       if (tile == TILE_NONE) break;
       flood_consume(a, sm, s, tile);
       consumer_sync();  // all results of the tile issued, all reads of the stage done
       if (threadIdx.x == 0) mbar_arrive(&sm.empty[s]);
+      waited += t1 - t0;
+      busy += clock64() - t1;
+    }
+    if (threadIdx.x == 0) {  // in units of 1024 cycles, summed over the CTAs
+      atomicAdd(&a.b.ctrl[FC_WAIT_KCYC], (uint32_t)(waited >> 10));
+      atomicAdd(&a.b.ctrl[FC_BUSY_KCYC], (uint32_t)(busy >> 10));
     }
   }
 }
@@ -626,9 +681,50 @@ int flood_bucket_shift(size_t nseeds, const ImageDims& d) {
 
 // The grid never exceeds the co-resident CTA count; no CTA waits for a particular other CTA (only for
 // the worklist to drain), so a plain launch is enough.
+// Tensor maps of a plan's arrival-time and image planes (host; the driver's encoder through the runtime).
+cudaError_t flood_make_tensor_maps(const FloodBuffers& b, const ImageDims& d, void* out_maps) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess) return e;
+  if (!fn || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+  CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(out_maps);
+  const cuuint32_t ones[2] = {1, 1};
+  {
+    const cuuint64_t dim[2] = {(cuuint64_t)d.t_pitch(), (cuuint64_t)d.t_rows() * (cuuint64_t)d.n_img};
+    const cuuint64_t stride[1] = {(cuuint64_t)d.t_pitch() * 4};
+    const cuuint32_t box[2] = {STG_W, STG_H};
+    if (((encode_fn)fn)(&maps[0], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, b.T, dim, stride, box, ones,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  {
+    const cuuint64_t dim[2] = {(cuuint64_t)d.pix_pitch(), (cuuint64_t)d.pix_rows() * (cuuint64_t)d.n_img};
+    const cuuint64_t stride[1] = {(cuuint64_t)d.pix_pitch()};
+    const cuuint32_t box[2] = {TILE_W, TILE_H};
+    if (((encode_fn)fn)(&maps[1], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b.pix, dim, stride, box, ones,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+
+// The grid never exceeds the co-resident CTA count; no CTA waits for a particular other CTA (only for
+// the worklist to drain), so a plain launch is enough.
 cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int bucket_shift, int grid,
-                         cudaStream_t s) {
-  FloodArgs a{b, d, check_overflow, bucket_shift};
+                         const void* tensor_maps, cudaStream_t s) {
+  FloodArgs a;
+  memcpy(&a.tmT, tensor_maps, sizeof(CUtensorMap));
+  memcpy(&a.tmP, (const char*)tensor_maps + sizeof(CUtensorMap), sizeof(CUtensorMap));
+  a.b = b;
+  a.d = d;
+  a.check_overflow = check_overflow;
+  a.bucket_shift = bucket_shift;
   const int want = d.tiles_total();
   const int g = want < grid ? (want > 0 ? want : 1) : grid;
   flood_kernel<<<g, FLOOD_THREADS, 0, s>>>(a);

@@ -12,6 +12,8 @@ enum FloodCtrl {
   FC_PHASES = 1,       // in-tile phases run                                      reset before every flood launch
   FC_STALE = 2,        // worklist entries dropped because nothing new had arrived  of a strip import)
   FC_IDLE = 3,         // idle polls of the producer warps
+  FC_WAIT_KCYC = 4,    // consumers: kilo-cycles waiting for a staged tile (tail at the end of the flood excluded)
+  FC_BUSY_KCYC = 5,    // consumers: kilo-cycles iterating
   FC_ERROR = 8,        // bit 0: seed out of bounds, bit 1: hop overflow, bit 2: orphan pixel, bit 3: flood watchdog
   FC_JUMP_FLAG0 = 9,   // [9..11] rotating "still unresolved" flags of the pointer jumping
   FC_JUMP_ROUNDS = 12,
@@ -77,7 +79,11 @@ cudaError_t launch_strip_count_pending(const uint32_t* lab, ImageDims d, int r0,
 cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseeds, size_t rows, size_t cols,
                                  cudaStream_t s);
 // bucket_shift: worklist bucket = wake-up level >> shift (flood_bucket_shift() picks it per run)
-cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int bucket_shift, int grid, cudaStream_t s);
+// tensor_maps: the two 128-byte maps made by flood_make_tensor_maps for this plan's planes
+constexpr size_t FLOOD_TENSOR_MAP_BYTES = 256;
+cudaError_t flood_make_tensor_maps(const FloodBuffers& b, const ImageDims& d, void* out_maps);
+cudaError_t launch_flood(FloodBuffers b, ImageDims d, int check_overflow, int bucket_shift, int grid,
+                         const void* tensor_maps, cudaStream_t s);
 int flood_bucket_shift(size_t nseeds, const ImageDims& d);
 cudaError_t launch_unpad_T(const uint32_t* Tp, ImageDims d, uint32_t* out, cudaStream_t s);
 
