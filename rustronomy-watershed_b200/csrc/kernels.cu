@@ -359,7 +359,15 @@ __global__ void __launch_bounds__(256) union_levels_kernel(MergeBuffers m, const
   }
 }
 
-int union_max_grid(int device) { return coop_max_grid((const void*)union_levels_kernel, 256, device); }
+// The kernel is bound by its 255 grid barriers and by dependent L2 round trips, not by thread count: after
+// the per-tile contraction a level holds ~3e4 edges, and a barrier over 2 CTAs per SM is much cheaper
+// than one over 8.
+int union_max_grid(int device) {
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int full = coop_max_grid((const void*)union_levels_kernel, 256, device);
+  return full < 2 * sms ? full : 2 * sms;
+}
 
 cudaError_t launch_union_levels(MergeBuffers m, const uint32_t* seed_off, int n_img, uint32_t lmax, int grid,
                                 cudaStream_t s) {
