@@ -181,7 +181,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (no "NCCL version" banner)
+        # stdout carries exactly one JSON line: whatever NCCL logs (its version banner at WARN and above)
+        # goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ws = load()
     ctx = ws.Context(local_rank)
