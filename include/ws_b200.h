@@ -276,9 +276,12 @@ ws_status ws_plan_strip_export_labels(ws_plan *plan, uint32_t *d_top, uint32_t *
  * still unresolved (loop over export / exchange / import until it is 0 on every strip).          */
 ws_status ws_plan_strip_import_labels(ws_plan *plan, const uint32_t *d_top, const uint32_t *d_bottom,
                                       size_t *pending);
-/* Spanning-forest edges of the strip's tiles as (colour a - 1, colour b - 1) uint32 pairs + a
- * level byte each (device pointers owned by the plan), and the number of this strip's colours
- * that are present on the canvas.                                                               */
+/* Forest edges of the strip's tiles as (colour a - 1, colour b - 1) uint32 pairs + a level byte
+ * each (device pointers owned by the plan), and the number of this strip's colours that are
+ * present on the canvas.  Bit 31 of the second word marks a FINAL edge: a certain edge of the
+ * global spanning forest (both basins lie inside the strip, contracted in their tile) that only
+ * has to be COUNTED at its level; the others are DEFERRED and go through ws_plan_union_edges.
+ * lakes(L) = colours present - unions at levels <= L - FINAL edges at levels <= L.              */
 ws_status ws_plan_strip_edges(ws_plan *plan, const void **d_ab, const void **d_w, size_t *n,
                               uint32_t *ndistinct);
 /* Kruskal over an edge list gathered from all strips: fills ws_plan_lake_counts()[0..255].      */

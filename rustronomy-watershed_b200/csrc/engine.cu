@@ -736,7 +736,7 @@ extern "C" ws_status ws_plan_strip_edges(ws_plan* p, const void** d_ab, const vo
     p->edges_cap = cap;
   }
   // labels are GLOBAL colours here (colour_base + i + 1), so the colour id is label - 1: offsets {0, ...}
-  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, 0, p->mb.red_ab, p->mb.red_w,
+  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, 1, p->mb.red_ab, p->mb.red_w,
                                    p->mb.red_count, s));
   WS_CUDA(ctx, launch_count_present(p->fb.lab, p->d, p->seeds, (uint32_t)p->nseeds, p->colour_base, p->mb.ndistinct, s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
@@ -780,7 +780,7 @@ extern "C" ws_status ws_plan_union_edges(ws_plan* p, const void* d_ab, const voi
   m.edges = p->union_edges;
   WS_CUDA(ctx, launch_red_sort((const uint2*)d_ab, (const uint8_t*)d_w, m.red_count, 1, p->d_strip_off, 1, m.level_hist,
                                m.level_cursor, m.fin_hist, m.edges, s));
-  WS_CUDA(ctx, cudaMemsetAsync(m.fin_hist, 0, 256 * sizeof(uint32_t), s));  // strips emit no FINAL edges
+  WS_CUDA(ctx, cudaMemsetAsync(m.fin_hist, 0, 256 * sizeof(uint32_t), s));  // every edge handed in is unioned
   WS_CUDA(ctx, launch_uf_reset(m, (uint32_t)ncolours, s));
   WS_CUDA(ctx, cudaMemcpyAsync(m.ndistinct, p->h_ctrl + FC_WORDS + 3, 4, cudaMemcpyHostToDevice, s));
   WS_CUDA(ctx, launch_union_levels(m, p->d_strip_off, 1, max_water_level, ctx->union_grid, s));

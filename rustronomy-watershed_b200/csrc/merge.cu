@@ -59,7 +59,7 @@ struct MergeSmem {
   uint32_t nlab, nout, gpos, first;
 };
 
-// `contract` = 0 (row strips: a strip's rim is not only its tiles' rims) skips stage 0.
+// `contract` = 0 skips stage 0 (every edge is emitted DEFERRED).
 __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t* __restrict__ lab,
                                                                   const uint8_t* __restrict__ lvl, ImageDims d,
                                                                   const uint32_t* __restrict__ seed_off, int contract,
@@ -147,8 +147,13 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     if (L[k] != 0u) {
       id = sm.a.table[slot[k]];
       const int r = i / MR_NW, c = i - r * MR_NW;
-      // rim: pixels whose up / left neighbour lies outside the tile, and the neighbour row / column itself
-      if (!contract || r == TILE_H || c == TILE_W || (r == 0 && r0 > 0) || (c == 0 && c0 > 0)) sm.flags[id] = 1;
+      // rim: pixels whose up / left neighbour lies outside the tile, and the neighbour row / column itself;
+      // in a row strip also the halo rows (the neighbouring strip's pixels) and the first owned row below a
+      // halo (its upward edges belong to the neighbouring strip)
+      const int gr = r0 + r;
+      if (!contract || r == TILE_H || c == TILE_W || (r == 0 && r0 > 0) || (c == 0 && c0 > 0) ||
+          (d.halo_top && gr <= 1) || (d.halo_bottom && gr == d.rows - 1))
+        sm.flags[id] = 1;
     }
     sm.b.n.lid[i] = (uint16_t)id;
   }

@@ -89,6 +89,9 @@ class LocalComm:
     def allgather_ints(self, local: Dict[int, int]) -> List[int]:
         return [local[s] for s in range(self.n_strips)]
 
+    def allreduce_sum_vec(self, v: np.ndarray) -> np.ndarray:
+        return v
+
     def allgather_edges(self, ab: List[torch.Tensor], w: List[torch.Tensor]):
         return torch.cat(ab) if ab else None, torch.cat(w) if w else None
 
@@ -130,6 +133,11 @@ class DistComm:
 
     def allreduce_sum(self, x: int) -> int:
         return self._reduce(x, self.dist.ReduceOp.SUM, self._dev)
+
+    def allreduce_sum_vec(self, v: np.ndarray) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.int64)).to(self._dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
 
     _dev = "cpu"
 
@@ -222,7 +230,12 @@ class CudaStrip:
         if n:
             self.ctx.d2d(ab.data_ptr(), d_ab, n * 8)
             self.ctx.d2d(w.data_ptr(), d_w, n)
-        return ab, w, nd
+        # FINAL edges (bit 31 of the second colour: negative as int32) are certain forest edges inside this
+        # strip: they are counted per level here and never leave the GPU; only the DEFERRED ones are gathered
+        fin = ab[:, 1] < 0
+        self.fin_hist = torch.bincount(w[fin].to(torch.int64), minlength=256).cpu().numpy().astype(np.int64)
+        keep = ~fin
+        return ab[keep].contiguous(), w[keep].contiguous(), nd
 
     def union(self, ab, w, ncolours: int, ndistinct: int, lmax: int) -> np.ndarray:
         n = int(ab.shape[0]) if ab is not None else 0
@@ -309,5 +322,12 @@ def solve(strips: Sequence, comm, kind: int = MERGING, max_water_level: int = 25
         ab_all, w_all = comm.allgather_edges(abs_, ws_)
         edges_total = int(ab_all.shape[0]) if ab_all is not None else 0
         first = by_id[sorted(by_id)[0]]
-        lake_counts = first.union(ab_all, w_all, int(bases[-1]), nd, max_water_level)[: max_water_level + 1].astype(np.uint64)
+        lake_counts = first.union(ab_all, w_all, int(bases[-1]), nd, max_water_level)[: max_water_level + 1].astype(np.int64)
+        # forest edges that were contracted inside a strip's tiles: counted, not unioned
+        fin = np.zeros(256, np.int64)
+        for sid in by_id:
+            fin += getattr(by_id[sid], "fin_hist", np.zeros(256, np.int64))
+        fin = comm.allreduce_sum_vec(fin)
+        lake_counts = (lake_counts - np.cumsum(fin)[: max_water_level + 1]).astype(np.uint64)
+        edges_total += int(fin.sum())
     return StripResult(lake_counts, flood_rounds, label_rounds, int(bases[-1]), edges_total)
