@@ -328,12 +328,20 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "flood_traffic.json"))).get(f"{args.field}_{S}")
     except Exception:
         pass
+    one_pass = npx * 5                                  # what ONE ideal pass would move: 1 B image in, 4 B arrival time out
     roofline = {"kernel": "flood_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "launch_ms": flood_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                # the same launch against the hardware instead of against the reference's 255 passes:
+                "dram_gbs": (traffic / (flood_avg_ms * 1e-3) / 1e9) if traffic else None,
+                "dram_frac_of_peak": (traffic / (flood_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "one_pass_bytes": one_pass, "one_pass_frac": one_pass / (flood_avg_ms * 1e-3) / 1e9 / peak,
+                "limiter": "issue rate of the in-tile relaxation (ncu: issue slots 67 % busy, SM throughput 81 %, "
+                           "consumer warps wait 3 % for staged tiles); see profiles/r01_j_flood_kernel_*",
                 "note": "algorithmic bytes = 9 B x pixels x 255 levels (one streaming pass per level, SURVEY 8(d)); "
                         "the kernel computes all levels in ONE arrival-time propagation, so frac > 1 is expected; "
-                        "traffic = measured DRAM bytes per launch (ncu), see profiles/"}
+                        "traffic = measured DRAM bytes per launch (ncu), see profiles/; one_pass_* = the bound of "
+                        "an ideal single pass (5 B per pixel), i.e. how far the launch is from pure streaming"}
 
     cpu = None
     if world == 1 and not args.no_cpu:

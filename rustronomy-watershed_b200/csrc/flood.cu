@@ -262,6 +262,7 @@ struct __align__(128) FloodSmem {
   uint8_t wpix[TILE_H * PIX_W];     // working image tile
   uint64_t full[FLOOD_STAGES], empty[FLOOD_STAGES];  // mbarriers of the ring
   uint32_t tile[FLOOD_STAGES];
+  uint32_t dirty[3];                // cells changed in a phase (rotating: written, read, cleared)
   uint32_t key[FLOOD_STAGES][4];               // per stage and direction: smallest value a changed edge pixel offers
                                     // the pixel facing it (KEY_NONE: that neighbour need not re-run)
 };
@@ -305,66 +306,89 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
 
   bool ovf = false;
   uint32_t nphase = 0;
-  for (;;) {
-    nphase += 2;
-    {  // ---- column phase: T(p) = max(A(p), 1 + min over the 4 neighbours) down then up ----
-      uint32_t t[ROWS_PER_THREAD], m[ROWS_PER_THREAD];
-      const uint32_t up = colp[-SM_W], dn = colp[ROWS_PER_THREAD * SM_W];
+  // Dirty cells.  The tile is 4 x 8 cells of 8 x 8 pixels (bit = cell row * 8 + cell column).  A warp
+  // iterates in a phase only if one of its four cells, or a cell next to them, changed in the previous
+  // phase -- otherwise every pixel it owns was verified against unchanged neighbours the last time it ran.
+  // After the first few phases of a tile, and in re-activations that only bring in one edge, most warps skip.
+  const uint32_t col_cells = 0xFu << (cgp * 8 + (warp & 1) * 4);  // column phase: rows cgp*8.., 32 columns
+  const uint32_t col_bit = 1u << (cgp * 8 + cl / 8);
+  const uint32_t row_cells = 0x01010101u << warp;                  // row phase: 32 rows, columns warp*8..
+  const uint32_t row_bit = 1u << ((rl / 8) * 8 + rgp);
+  uint32_t active = 0xFFFFFFFFu;  // cells that changed in the previous phase, dilated by one cell
+  if (tid == 0) sm.dirty[0] = sm.dirty[1] = sm.dirty[2] = 0u;
+  consumer_sync();
+  for (uint32_t ph = 0;; ++ph) {
+    ++nphase;
+    uint32_t it = 0;
+    if ((ph & 1u) == 0u) {
+      if (active & col_cells) {
+        // ---- column phase: T(p) = max(A(p), 1 + min over the 4 neighbours) down then up ----
+        uint32_t t[ROWS_PER_THREAD], m[ROWS_PER_THREAD];
+        const uint32_t up = colp[-SM_W], dn = colp[ROWS_PER_THREAD * SM_W];
 #pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        t[i] = colp[i * SM_W];
-        m[i] = min(colp[i * SM_W - 1], colp[i * SM_W + 1]);
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          t[i] = colp[i * SM_W];
+          m[i] = min(colp[i * SM_W - 1], colp[i * SM_W + 1]);
+        }
+        uint32_t prev = up;
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          const uint32_t nb = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : dn;
+          const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ac[i]);  // max(A, 1 + min3)
+          if (n < t[i]) { t[i] = n; it |= 1u << i; }
+          prev = t[i];
+        }
+        prev = dn;
+#pragma unroll
+        for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
+          const uint32_t nb = (i > 0) ? t[i - 1] : up;
+          const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ac[i]);  // max(A, 1 + min3)
+          if (n < t[i]) { t[i] = n; it |= 1u << i; }
+          prev = t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i)
+          if (it & (1u << i)) colp[i * SM_W] = t[i];
+        const uint32_t wm = __reduce_or_sync(0xffffffffu, it ? col_bit : 0u);
+        if (lane == 0 && wm) atomicOr(&sm.dirty[ph % 3u], wm);
       }
-      uint32_t it = 0, prev = up;
+    } else {
+      if (active & row_cells) {
+        // ---- row phase: right then left ----------------------------------------------------
+        uint32_t t[ROWS_PER_THREAD], m[ROWS_PER_THREAD];
+        const uint32_t lf = rowp[-1], rt = rowp[ROWS_PER_THREAD];
 #pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const uint32_t nb = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : dn;
-        const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ac[i]);  // max(A, 1 + min3)
-        if (n < t[i]) { t[i] = n; it |= 1u << i; ovf |= ((n & HOP_MASK) == 0u); }
-        prev = t[i];
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          t[i] = rowp[i];
+          m[i] = min(rowp[i - SM_W], rowp[i + SM_W]);
+        }
+        uint32_t prev = lf;
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+          const uint32_t nb = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : rt;
+          const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ar[i]);
+          if (n < t[i]) { t[i] = n; it |= 1u << i; }
+          prev = t[i];
+        }
+        prev = rt;
+#pragma unroll
+        for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
+          const uint32_t nb = (i > 0) ? t[i - 1] : lf;
+          const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ar[i]);
+          if (n < t[i]) { t[i] = n; it |= 1u << i; }
+          prev = t[i];
+        }
+#pragma unroll
+        for (int i = 0; i < ROWS_PER_THREAD; ++i)
+          if (it & (1u << i)) rowp[i] = t[i];
+        const uint32_t wm = __reduce_or_sync(0xffffffffu, it ? row_bit : 0u);
+        if (lane == 0 && wm) atomicOr(&sm.dirty[ph % 3u], wm);
       }
-      prev = dn;
-#pragma unroll
-      for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
-        const uint32_t nb = (i > 0) ? t[i - 1] : up;
-        const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ac[i]);  // max(A, 1 + min3)
-        if (n < t[i]) { t[i] = n; it |= 1u << i; ovf |= ((n & HOP_MASK) == 0u); }
-        prev = t[i];
-      }
-#pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i)
-        if (it & (1u << i)) colp[i * SM_W] = t[i];
-      if (!consumer_sync_or(it != 0u)) break;
     }
-    {  // ---- row phase: right then left ----------------------------------------------------
-      uint32_t t[ROWS_PER_THREAD], m[ROWS_PER_THREAD];
-      const uint32_t lf = rowp[-1], rt = rowp[ROWS_PER_THREAD];
-#pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        t[i] = rowp[i];
-        m[i] = min(rowp[i - SM_W], rowp[i + SM_W]);
-      }
-      uint32_t it = 0, prev = lf;
-#pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        const uint32_t nb = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : rt;
-        const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ar[i]);
-        if (n < t[i]) { t[i] = n; it |= 1u << i; ovf |= ((n & HOP_MASK) == 0u); }
-        prev = t[i];
-      }
-      prev = rt;
-#pragma unroll
-      for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
-        const uint32_t nb = (i > 0) ? t[i - 1] : lf;
-        const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ar[i]);
-        if (n < t[i]) { t[i] = n; it |= 1u << i; ovf |= ((n & HOP_MASK) == 0u); }
-        prev = t[i];
-      }
-#pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i)
-        if (it & (1u << i)) rowp[i] = t[i];
-      if (!consumer_sync_or(it != 0u)) break;
-    }
+    if (tid == 0) sm.dirty[(ph + 1u) % 3u] = 0u;  // last read after the barrier of phase ph - 2
+    if (!consumer_sync_or(it != 0u)) break;
+    const uint32_t dm = sm.dirty[ph % 3u];
+    active = dm | ((dm & ~0x80808080u) << 1) | ((dm & ~0x01010101u) >> 1) | (dm << 8) | (dm >> 8);
   }
 
   // write back what changed against the staged copy (column ownership: coalesced along rows)
@@ -385,6 +409,10 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     const uint32_t v = colp[i * SM_W];
     if (v != st.T[(cgp * ROWS_PER_THREAD + i + 1) * STG_W + cl + T_PAD_L]) {
+      // A hop counter that ran past 2^24 - 1 carries into the level and leaves hop == 0 behind: the pixel
+      // where that happens keeps this value (everything after it is built on it), so looking at the values
+      // that are written back is enough -- no test inside the relaxation.
+      ovf |= ((v & HOP_MASK) == 0u);
       atomicMin(Tg + (size_t)i * tp, v);  // result unused: a fire-and-forget RED.MIN (measured: same time as st)
       if (cl == 0 && v + 1u < colp[i * SM_W - 1]) kl = min(kl, v + 1u);
       if (cl == TILE_W - 1 && v + 1u < colp[i * SM_W + 1]) kr = min(kr, v + 1u);
