@@ -16,6 +16,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace ws;
@@ -913,14 +914,42 @@ ws_status host_run(ws_ctx* ctx, const ws_config* cfg, const ws_image* img, const
 // compute stream, device->host copy on the copy stream, double buffered.  `sink` receives
 // (level, host pointer valid until the next but one call) -- or the copy goes straight to
 // `direct` + level * npx when that is given.
+// host copy with several threads (one core moves ~10 GB/s, the D2H link ~55 GB/s)
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t nt = std::max<size_t>(1, std::min<size_t>(16, std::min<size_t>(hw ? hw : 1, bytes >> 22)));
+  if (nt == 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t chunk = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+  for (size_t t = 0; t < nt; ++t) {
+    const size_t lo = t * chunk;
+    if (lo >= bytes) break;
+    const size_t n = std::min(chunk, bytes - lo);
+    th.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, n); });
+  }
+  for (auto& t : th) t.join();
+}
+
 template <typename Sink>
 ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint64_t* direct, Sink sink) {
   ws_plan* p = hr.plan;
   const size_t npx = hr.npx;
   const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
+  // Caller memory that is page-locked takes the copies directly.  Pageable memory would make the driver
+  // stage every copy itself (~20 GB/s measured): go through our own pinned double buffer instead and move
+  // level l - 1 out with several host threads while level l crosses the link.
+  bool staged = true;
+  if (direct) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, direct) == cudaSuccess && at.type == cudaMemoryTypeHost) staged = false;
+    cudaGetLastError();
+  }
   for (int i = 0; i < 2; ++i) {
     WS_TRY(grow(ctx, ctx->d_out[i], ctx->d_out_cap[i], npx));
-    if (!direct && ctx->h_pin_cap[i] < npx) {
+    if (staged && ctx->h_pin_cap[i] < npx) {
       if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
       ctx->h_pin[i] = nullptr; ctx->h_pin_cap[i] = 0;
       WS_CUDA(ctx, cudaMallocHost((void**)&ctx->h_pin[i], npx * 8));
@@ -935,14 +964,15 @@ ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint6
       WS_TRY(ws_plan_snapshot(p, kind, 0, (uint8_t)l, ctx->d_out[buf]));
       WS_CUDA(ctx, cudaEventRecord(ctx->ev_ready[buf], ctx->stream));
       WS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[buf], 0));
-      uint64_t* dst = direct ? direct + (size_t)l * npx : ctx->h_pin[buf];
+      uint64_t* dst = staged ? ctx->h_pin[buf] : direct + (size_t)l * npx;
       WS_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_out[buf], npx * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
       WS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
     }
-    if (l >= 1 && !direct) {  // hand level l-1 to the sink while level l is in flight
+    if (l >= 1 && staged) {  // hand level l-1 on while level l is in flight
       const int pb = (l - 1) & 1;
       WS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[pb]));
-      sink((uint8_t)(l - 1), ctx->h_pin[pb]);
+      if (direct) parallel_memcpy(direct + (size_t)(l - 1) * npx, ctx->h_pin[pb], npx * 8);
+      else sink((uint8_t)(l - 1), ctx->h_pin[pb]);
     }
   }
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
