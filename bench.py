@@ -181,10 +181,20 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: whatever NCCL logs (its version banner at WARN and above)
-        # goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: NCCL prints its version banner to stdout when the first
+        # communicator comes up (at NCCL_DEBUG=VERSION and above), so file descriptor 1 points at stderr
+        # until the first collective is through
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     ws = load()
     ctx = ws.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
