@@ -315,7 +315,7 @@ def main():
             t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        h2d = 2 * (npx + nseeds * 8)                   # image + u32 seed pairs, both transforms
+        h2d = 2 * (npx + nseeds * 16)                  # image + (usize, usize) seed pairs as the API takes them, both transforms
         d2h = npx * 8 + 2 * LEVELS * 4 + 1024          # u64 labels + counts + level histogram
         e2e = {"value": world * args.steps * px_levels_step / e2e_s / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
