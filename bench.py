@@ -346,8 +346,8 @@ def main():
                 "dram_gbs": (traffic / (flood_avg_ms * 1e-3) / 1e9) if traffic else None,
                 "dram_frac_of_peak": (traffic / (flood_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "one_pass_bytes": one_pass, "one_pass_frac": one_pass / (flood_avg_ms * 1e-3) / 1e9 / peak,
-                "limiter": "issue rate of the in-tile relaxation (ncu: issue slots 67 % busy, SM throughput 81 %, "
-                           "consumer warps wait 3 % for staged tiles); see profiles/r01_j_flood_kernel_*",
+                "limiter": "issue rate of the in-tile relaxation (ncu: issue slots 66 % busy, 2.7 G warp instructions, "
+                           "consumer warps wait 4 % for staged tiles); see profiles/r01_k_flood_kernel_*",
                 "note": "algorithmic bytes = 9 B x pixels x 255 levels (one streaming pass per level, SURVEY 8(d)); "
                         "the kernel computes all levels in ONE arrival-time propagation, so frac > 1 is expected; "
                         "traffic = measured DRAM bytes per launch (ncu), see profiles/; one_pass_* = the bound of "
