@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256) union_levels_kernel(MergeBuffers m, const
 
 // The kernel is bound by its 255 grid barriers and by dependent L2 round trips, not by thread count: after
 // the per-tile contraction a level holds ~3e4 edges, and a barrier over 2 CTAs per SM is much cheaper
-// than one over 8.
+// than one over 8 (merge phase, uniform 16384^2: 1 CTA per SM 10.2 ms, 2 per SM 9.6 ms, 8 per SM 9.8 ms).
 int union_max_grid(int device) {
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
