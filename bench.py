@@ -60,6 +60,27 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_near_gpu(index: int) -> str:
+    """Pin this process to the CPUs next to GPU `index` (NVML's ideal affinity) BEFORE any host buffer is
+    allocated, so that pinned memory is first-touched on the GPU's NUMA node.  With 8 ranks on a two-socket
+    host, unbound ranks put their staging buffers wherever the launcher left them and half of the host<->device
+    traffic crosses the socket link.  Returns a one-line description for the bench record."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} CPUs local to GPU {index} ({cpus[0]}..{cpus[-1]})"
+        return "no local CPU set reported"
+    except Exception as e:  # no NVML / no permission: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -178,6 +199,8 @@ def main():
     if args.warmup < 3:
         print(f"note: --warmup {args.warmup} < 3 breaks the timing rules", file=sys.stderr)
 
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -355,6 +378,7 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)              # the CPU baseline gets every core the box gives us
         v, dt, thr = cpu_sample(args.field, S, args.cpu_crop, 0)
         cpu = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
                "sample": f"{args.cpu_crop}x{args.cpu_crop} {args.field} crop, segmenting + merging, {dt:.1f} s; "
@@ -367,7 +391,7 @@ def main():
         "config": {"workload": f"{S}x{S} u8 {args.field} field per GPU, segmenting + merging transform, 255 levels",
                    "seeds": nseeds, "seed_finding_ms": seed_ms, "l2": "inputs larger than L2 (no flush needed)"
                    if npx * 9 > 126e6 else "inputs fit in L2",
-                   "parallelism": f"{world} independent fields (shards, no collective)"},
+                   "parallelism": f"{world} independent fields (shards, no collective)", "host_binding": numa},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         "phases_ms_last_step": {"segmenting": phases[0], "merging": phases[1]},
         "extra_smooth_field": extra,
