@@ -3,10 +3,11 @@
 //
 // Pipeline of one run (all on the context's stream, no host round trip except
 // where noted):
-//   fill_state -> seed_init -> flood (persistent, cooperative)
-//   -> parent -> jump (persistent, cooperative)                      [labels + levels]
-//   merging only: merge_reduce (per-tile Kruskal in shared memory) -> red_hist -> edge_scan ->
-//   red_scatter -> uf_init -> union_levels (persistent, cooperative) -> lake_counts
+//   fill_state -> seed_init -> flood (persistent, asynchronous worklist)
+//   -> label_tile -> rim_jump (persistent, cooperative) -> label_finish      [labels + levels]
+//   merging only: merge_reduce (per-tile contraction + spanning forest in shared memory) -> red_hist ->
+//   edge_scan -> red_scatter -> uf_init -> union_levels (persistent, cooperative) -> lake_counts;
+//   the merge tree for per-level representatives is built on demand (plan_build_tree)
 #include "../../include/ws_b200.h"
 #include "kernels.cuh"
 
