@@ -279,6 +279,19 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t x) {
   return x;
 }
 
+// Both roots at once: the two walks are independent chains of dependent loads (L2 or DRAM round trips),
+// and a level of union_levels is latency bound -- issue the hops of both walks together.
+__device__ __forceinline__ void uf_find2(uint32_t* parent, uint32_t& a, uint32_t& b) {
+  uint32_t pa = ld_cg(parent + a), pb = ld_cg(parent + b);
+  while (pa != a || pb != b) {
+    const uint32_t ga = ld_cg(parent + pa), gb = ld_cg(parent + pb);  // (a root's parent is itself)
+    if (pa != a && ga != pa) st_cg(parent + a, ga);  // path halving; only ever points at an ancestor
+    if (pb != b && gb != pb) st_cg(parent + b, gb);
+    a = pa; pa = ga;
+    b = pb; pb = gb;
+  }
+}
+
 constexpr uint32_t UNION_SMALL_LIMIT = 1u << 18;  // edge lists up to this size go through ONE CTA
 
 // Small edge lists (e.g. a 512x512 field: ~4e4 forest edges): one CTA, a CTA barrier per level
@@ -332,8 +345,7 @@ __global__ void __launch_bounds__(256) union_levels_kernel(MergeBuffers m, const
       const uint2 e = m.edges[i];
       uint32_t a = e.x, b = e.y;
       for (;;) {
-        a = uf_find(m.parent, a);
-        b = uf_find(m.parent, b);
+        uf_find2(m.parent, a, b);
         if (a == b) break;
         if (a < b) { const uint32_t t = a; a = b; b = t; }   // hook the larger root under the smaller
         if (atomicCAS(m.parent + a, a, b) == a) {
