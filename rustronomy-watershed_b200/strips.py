@@ -268,16 +268,26 @@ class StripResult:
     label_rounds: int
     nseeds_total: int
     edges_total: int
+    phase_s: Optional[dict] = None        # wall seconds per phase of the protocol (this process)
 
 
 def solve(strips: Sequence, comm, kind: int = MERGING, max_water_level: int = 254, max_rounds: int = 100000) -> StripResult:
     """Run the protocol over the strips this process holds (`strips[i]` has geometry sid = comm.local_ids[i])."""
+    import time
     by_id = {s.geom.sid: s for s in strips}
     assert sorted(by_id) == sorted(comm.local_ids)
+    phase_s, t_last = {}, time.perf_counter()
+
+    def lap(name):
+        nonlocal t_last
+        now = time.perf_counter()
+        phase_s[name] = phase_s.get(name, 0.0) + now - t_last
+        t_last = now
     counts = comm.allgather_ints({sid: s.nseeds for sid, s in by_id.items()})
     bases = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     for sid, s in by_id.items():
         s.begin(kind, max_water_level, int(bases[sid]))
+    lap("begin: state, seeds, first flood")
 
     def exchange(exporter, importer, reducer, stop_when):
         rounds = 0
@@ -301,14 +311,17 @@ def solve(strips: Sequence, comm, kind: int = MERGING, max_water_level: int = 25
 
     flood_rounds = exchange(lambda s: s.export_times(), lambda s, t, b: int(s.import_times(t, b)),
                             max, lambda acc: comm.allreduce_max(acc) == 0)
+    lap("arrival-time exchange rounds")
     for s in by_id.values():
         s.labels()
+    lap("labels")
     label_rounds = exchange(lambda s: s.export_labels(), lambda s, t, b: s.import_labels(t, b),
                             lambda a, b: a + b, lambda acc: comm.allreduce_sum(acc) == 0)
     # Every OWNED pixel is resolved now, but a halo row still shows what its owner exported at the start
     # of the last round; the edges towards the halo rows need the final words: one more exchange.
     label_rounds += exchange(lambda s: s.export_labels(), lambda s, t, b: s.import_labels(t, b),
                              lambda a, b: a + b, lambda acc: True)
+    lap("label exchange rounds")
 
     lake_counts, edges_total = None, 0
     if kind == MERGING:
@@ -330,4 +343,5 @@ def solve(strips: Sequence, comm, kind: int = MERGING, max_water_level: int = 25
         fin = comm.allreduce_sum_vec(fin)
         lake_counts = (lake_counts - np.cumsum(fin)[: max_water_level + 1]).astype(np.uint64)
         edges_total += int(fin.sum())
-    return StripResult(lake_counts, flood_rounds, label_rounds, int(bases[-1]), edges_total)
+        lap("forest edges, gather, union")
+    return StripResult(lake_counts, flood_rounds, label_rounds, int(bases[-1]), edges_total, phase_s)

@@ -66,7 +66,8 @@ def main():
            "Mpx_levels_per_s": S * S * 255 / min(times) / 1e6, "flood_exchange_rounds": res.flood_rounds,
            "label_exchange_rounds": res.label_rounds, "seeds": res.nseeds_total, "forest_edges": res.edges_total,
            "lakes_0_64_127_191_254": [int(res.lake_counts[i]) for i in (0, 64, 127, 191, 254)],
-           "halo_bytes_per_round_per_neighbour": S * 4}
+           "halo_bytes_per_round_per_neighbour": S * 4,
+           "phase_ms_rank0_last_rep": {k: round(1e3 * v, 3) for k, v in (res.phase_s or {}).items()}}
     if args.check:
         lab = torch.from_numpy(strip.owned_labels().astype(np.int32)).cuda()
         gathered = [torch.empty((parts[r][1] - parts[r][0], S), dtype=torch.int32, device="cuda") for r in range(world)]
