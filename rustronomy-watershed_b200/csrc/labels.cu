@@ -30,7 +30,10 @@ constexpr int LT_THREADS = 256;
 constexpr int LT_W = STG_W;       // staged arrival times: rows of 72 words (image columns c0-4 .. c0+67)
 constexpr int LT_H = TILE_H + 2;
 constexpr int LT_C0 = T_PAD_L;    // staged column of the tile's column 0
-constexpr uint16_t LT_TERMINAL = 0xFFFFu;
+// working word of a pixel: LT_LOCAL | next pixel of its chain inside the tile (bits 31..30 = 01); anything else
+// is final: a colour (bit 31 set; bit 30 may belong to the colour) or a rim reference (< 2^28)
+constexpr uint32_t LT_LOCAL = 0x40000000u;
+__device__ __forceinline__ bool lt_is_local(uint32_t w) { return (w >> 30) == 1u; }
 constexpr int RIM_PER_TILE = 2 * TILE_W + 2 * (TILE_H - 2);  // 188
 
 size_t rim_words(const ImageDims& d) { return (size_t)d.tiles_total() * RIM_PER_TILE + 2 * (size_t)d.cols; }
@@ -45,8 +48,7 @@ __device__ __forceinline__ int rim_index(int lr, int lc) {
 
 struct __align__(128) LabelSmem {
   uint32_t T[LT_H * LT_W];
-  uint32_t term[TILE_H * TILE_W];  // final word of the pixel once nxt == LT_TERMINAL
-  uint16_t nxt[TILE_H * TILE_W];   // next pixel of the chain inside the tile
+  uint32_t w[TILE_H * TILE_W];     // per pixel: LT_LOCAL | next pixel inside the tile, or its final word
   uint64_t bar;
 };
 
@@ -81,7 +83,6 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
     const int li = lr * TILE_W + lc;
     const int r = r0 + lr, c = c0 + lc;
     uint32_t term = LAB_RESOLVED;  // UNCOLOURED
-    uint16_t nx = LT_TERMINAL;
     if (r < d.rows && c < d.cols) {
       const uint32_t* t = sm.T + (lr + 1) * LT_W + lc + LT_C0;
       const uint32_t tv = t[0];
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
         if (dr == 0 && dc == 0) {
           // leave UNCOLOURED
         } else if (pr >= 0 && pr < TILE_H && pc >= 0 && pc < TILE_W) {
-          nx = (uint16_t)(pr * TILE_W + pc);
+          term = LT_LOCAL | (uint32_t)(pr * TILE_W + pc);
         } else {
           // the chain leaves the tile here, onto the rim of the neighbouring tile
           const int ntile = blockIdx.x + dr * d.tiles_x + dc;
@@ -115,37 +116,28 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
         }
       }
     }
-    sm.term[li] = term;
-    sm.nxt[li] = nx;
+    sm.w[li] = term;
   }
   __syncthreads();
 
   // pointer jumping inside the tile (reads and writes separated by barriers); `act` = my pixels that
   // still hold an in-tile pointer
-  uint32_t act = 0;
+  uint32_t act = 0, cur[ROWS_PER_THREAD];
 #pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i)
-    if (sm.nxt[(g * ROWS_PER_THREAD + i) * TILE_W + lc] != LT_TERMINAL) act |= 1u << i;
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+    cur[i] = sm.w[(g * ROWS_PER_THREAD + i) * TILE_W + lc];
+    if (lt_is_local(cur[i])) act |= 1u << i;
+  }
   while (__syncthreads_or(act != 0u)) {
-    uint16_t n2[ROWS_PER_THREAD];
-    uint32_t t2[ROWS_PER_THREAD];
 #pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-      if (!(act & (1u << i))) continue;
-      const uint16_t n = sm.nxt[(g * ROWS_PER_THREAD + i) * TILE_W + lc];
-      n2[i] = sm.nxt[n];
-      t2[i] = sm.term[n];
-    }
+    for (int i = 0; i < ROWS_PER_THREAD; ++i)
+      if (act & (1u << i)) cur[i] = sm.w[cur[i] & (TILE_H * TILE_W - 1)];  // my successor's word: its successor, or the end
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < ROWS_PER_THREAD; ++i) {
       if (!(act & (1u << i))) continue;
-      const int li = (g * ROWS_PER_THREAD + i) * TILE_W + lc;
-      sm.nxt[li] = n2[i];
-      if (n2[i] == LT_TERMINAL) {
-        sm.term[li] = t2[i];
-        act &= ~(1u << i);
-      }
+      sm.w[(g * ROWS_PER_THREAD + i) * TILE_W + lc] = cur[i];
+      if (!lt_is_local(cur[i])) act &= ~(1u << i);
     }
   }
 
@@ -153,7 +145,7 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     const int lr = g * ROWS_PER_THREAD + i;
     const int r = r0 + lr, c = c0 + lc;
-    if (r < d.rows && c < d.cols) __stcg(b.lab + base + (size_t)r * d.cols + c, sm.term[lr * TILE_W + lc]);
+    if (r < d.rows && c < d.cols) __stcg(b.lab + base + (size_t)r * d.cols + c, sm.w[lr * TILE_W + lc]);
   }
   // the tile's rim, compact (pixels outside the image: UNCOLOURED, so that every entry is defined)
   if (tid < RIM_PER_TILE) {
@@ -163,7 +155,7 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
     else if (tid < 2 * TILE_W + TILE_H - 2) { lr = 1 + (tid - 2 * TILE_W); lcc = 0; }
     else { lr = 1 + (tid - 2 * TILE_W - (TILE_H - 2)); lcc = TILE_W - 1; }
     const bool in = (r0 + lr < d.rows) && (c0 + lcc < d.cols);
-    __stcg(b.rim + (size_t)blockIdx.x * RIM_PER_TILE + tid, in ? sm.term[lr * TILE_W + lcc] : LAB_RESOLVED);
+    __stcg(b.rim + (size_t)blockIdx.x * RIM_PER_TILE + tid, in ? sm.w[lr * TILE_W + lcc] : LAB_RESOLVED);
   }
 }
 
