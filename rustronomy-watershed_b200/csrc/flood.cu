@@ -433,7 +433,6 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
 
 constexpr int POP_MAX = 4;  // tiles one claim may take when the worklist is long
 
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 // Claim tiles from the best (lowest) non-empty bucket (warp-collective): up to POP_MAX when that
 // bucket holds far more entries than there are CTAs -- the claim is a chain of five dependent L2 round
@@ -528,7 +527,10 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
         // while work exists); the fence orders that, and the consumers' results (ordered before us by
         // the mbarrier), before the marks and appends below.  The surplus is returned afterwards.
         if (lane == 0) atomicAdd(&a.b.ctrl[FC_OUTSTANDING], 3u);  // + 4 possible entries - this tile
-        fence_acq_rel_gpu();
+        // Sequentially consistent fence (MEMBAR.SC.GPU), not just acquire-release: when the mark below finds
+        // the neighbour already dirty and queued it only READS the mask word, and "my results are visible
+        // to whoever takes that entry afterwards" is then a store-buffering shape that needs SC on this side.
+        __threadfence();
         const uint32_t bk = flood_bucket(k >> 24, a.bucket_shift);
         uint32_t nb = TILE_NONE;
         if (k != KEY_NONE) {
