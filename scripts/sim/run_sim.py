@@ -4,7 +4,17 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
 import fieldgen
 
-lib = ctypes.CDLL("/tmp/flood_sim.so")
+def _build():
+    """gcc -O3 -shared flood_sim.c into the temp dir (rebuilt when the source is newer)."""
+    import subprocess, tempfile
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "flood_sim.c")
+    out = os.path.join(tempfile.gettempdir(), f"ws_flood_sim_{os.getuid()}.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.run(["gcc", "-O3", "-shared", "-fPIC", "-o", out, src], check=True)
+    return out
+
+
+lib = ctypes.CDLL(_build())
 def maxima(img):
     a = img.astype(np.int16)
     c = a[1:-1, 1:-1]
