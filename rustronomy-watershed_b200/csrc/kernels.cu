@@ -81,37 +81,55 @@ __global__ void __launch_bounds__(256) minima_count_kernel(const uint8_t* __rest
   }
 }
 
-// Single-CTA exclusive scan (n_chunks is at most a few 100k; ~tens of microseconds).
+// Single-CTA exclusive scan (n_chunks is at most a few 100k).  Every warp owns a contiguous block of the
+// array and walks it 32 values at a time -- coalesced loads, a shuffle scan per step -- instead of every
+// thread walking its own 1 KB-strided run (the first version: 0.45 ms for 262144 counts, now 0.10 ms).
 __global__ void __launch_bounds__(1024) minima_scan_kernel(uint32_t* __restrict__ v, size_t n, ImageDims d,
                                                            uint32_t* __restrict__ seed_off,
                                                            uint32_t* __restrict__ total) {
-  __shared__ uint32_t s_part[1024];
-  const size_t per = (n + 1023) / 1024;
-  const size_t lo = min(n, (size_t)threadIdx.x * per), hi = min(n, lo + per);
+  __shared__ uint32_t s_warp[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t per = ((n + 31) / 32 + 31) / 32 * 32;  // values per warp, a multiple of 32
+  const size_t lo = min(n, (size_t)warp * per), hi = min(n, lo + per);
+  // pass 1: the warp's total
   uint32_t sum = 0;
-  for (size_t i = lo; i < hi; ++i) sum += v[i];
-  s_part[threadIdx.x] = sum;
+  for (size_t i = lo + lane; i < hi; i += 32) sum += v[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_warp[warp] = sum;
   __syncthreads();
-  // Hillis-Steele inclusive scan over the 1024 partials
-  for (int o = 1; o < 1024; o <<= 1) {
-    uint32_t add = (threadIdx.x >= (unsigned)o) ? s_part[threadIdx.x - o] : 0u;
-    __syncthreads();
-    s_part[threadIdx.x] += add;
-    __syncthreads();
-  }
-  uint32_t run = (threadIdx.x == 0) ? 0u : s_part[threadIdx.x - 1];
-  for (size_t i = lo; i < hi; ++i) {
-    const uint32_t c = v[i];
-    v[i] = run;
-    run += c;
+  if (warp == 0) {  // exclusive scan of the 32 warp totals
+    const uint32_t mine = s_warp[lane];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    s_warp[lane] = incl - mine;
+    if (lane == 31) total[0] = incl;
   }
   __syncthreads();
-  if (threadIdx.x == 0) total[0] = s_part[1023];
+  // pass 2: exclusive scan inside the warp's block
+  uint32_t run = s_warp[warp];
+  for (size_t i0 = lo; i0 < hi; i0 += 32) {
+    const size_t i = i0 + lane;
+    const uint32_t c = i < hi ? v[i] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (i < hi) v[i] = run + incl - c;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncthreads();
   // offsets of the slices = offset of each slice's first chunk
   const int segs = (d.cols + MINIMA_CHUNK - 1) / MINIMA_CHUNK;
   const size_t per_img = (size_t)d.rows * segs;
   for (int b = threadIdx.x; b <= d.n_img; b += 1024)
-    seed_off[b] = (b == d.n_img) ? s_part[1023] : v[(size_t)b * per_img];
+    seed_off[b] = (b == d.n_img) ? total[0] : v[(size_t)b * per_img];
 }
 
 __global__ void __launch_bounds__(256) minima_write_kernel(const uint8_t* __restrict__ img, ImageDims d,
