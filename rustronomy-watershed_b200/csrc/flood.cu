@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
       }
       // claim a tile; while there is none, finish the other stage (its pushes may be the next work)
       uint32_t tile = TILE_NONE;
-      uint32_t idle = 0;
+      uint32_t idle = 0, stalled = 0, seen_activations = 0xFFFFFFFFu;
       for (;;) {
         if (q_i < q_n) {
           tile = __shfl_sync(0xffffffffu, q_tile, q_i);
@@ -598,7 +598,17 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
           break;  // nothing queued, nothing in flight anywhere: the fixed point is reached
         }
         __nanosleep(100);
-        if (++idle > (1u << 25)) atomicOr(&a.b.ctrl[FC_ERROR], 16u);  // watchdog (> 10 s idle): never hang the device
+        // watchdog: never hang the device -- but only when NOTHING moves any more (a flood that is one long
+        // dependency chain keeps most CTAs idle for as long as it takes)
+        if ((++idle & 0xFFFFu) == 0u) {
+          const uint32_t act = ld_poll(&a.b.ctrl[FC_ACTIVATIONS]);
+          if (act != seen_activations) {
+            seen_activations = act;
+            stalled = 0;
+          } else if (++stalled > 256u) {  // ~256 x 65536 polls (tens of seconds) without a single tile claimed anywhere
+            atomicOr(&a.b.ctrl[FC_ERROR], 16u);
+          }
+        }
       }
       if (lane == 0) {
         if (idle) atomicAdd(&a.b.ctrl[FC_IDLE], idle);

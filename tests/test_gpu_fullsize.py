@@ -113,3 +113,37 @@ def test_lake_counts_against_merge_tree_full_size(S, field):
         assert lakes == counts[level], (level, lakes, int(counts[level]))
         del u
     plan.close()
+
+
+def test_one_long_dependency_chain():
+    """A serpentine corridor: the whole flood is ONE chain of ~half a million dependent hops through ~8000 tile
+    visits, almost every CTA idles all the time (the worklist's idle / termination path), and the answer is
+    known in closed form: the hop count along the corridor."""
+    S = 1024
+    ws = load()
+    img = fieldgen.maze(S, S)
+    ctx = ws.default_context()
+    plan = ws.Plan(ctx, 1, S, S)
+    d_img = torch.from_numpy(img).cuda()
+    off = torch.tensor([0, 1], dtype=torch.int32, device="cuda")
+    seeds = torch.tensor([[1, 1]], dtype=torch.int32, device="cuda")
+    plan.run(0, 254, d_img.data_ptr(), seeds.data_ptr(), off.data_ptr(), 1)
+    T = _u32(plan.arrival_times_ptr, (S, S)).cpu().numpy()
+    lab = (_u32(plan.labels_ptr, (S, S)) & 0x7FFFFFFF).cpu().numpy()
+    # walk the corridor on the host: the k-th pixel after the seed floods in pass k of level 0
+    open_px = (img == 0)
+    open_px[0, :] = open_px[-1, :] = False
+    open_px[:, 0] = open_px[:, -1] = False
+    expect = np.full((S, S), INF, np.int64)
+    r, c, k, prev = 1, 1, 0, None
+    while True:
+        expect[r, c] = k
+        nxt = [(rr, cc) for rr, cc in ((r + 1, c), (r, c + 1), (r, c - 1), (r - 1, c))
+               if open_px[rr, cc] and (rr, cc) != prev and expect[rr, cc] == INF]
+        if not nxt:
+            break
+        prev, (r, c), k = (r, c), nxt[0], k + 1
+    assert k > 400000
+    assert np.array_equal(np.minimum(T, INF), expect)
+    assert np.array_equal(lab, (expect < INF).astype(np.int64))
+    plan.close()
