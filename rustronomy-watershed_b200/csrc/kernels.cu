@@ -16,42 +16,77 @@ namespace ws {
 // ===========================================================================
 // K1  find_local_minima  (lib.rs:1178-1197)
 //
-// One CTA = one row segment of MINIMA_CHUNK columns, 4 pixels per thread.
-// Chunks are numbered row-major (slice, row, segment), so an exclusive scan of
-// the per-chunk counts followed by an in-chunk rank reproduces the row-major
-// order of the reference's `collect()`.
+// One CTA = one row segment of MINIMA_CHUNK = 4096 columns; a thread handles MINIMA_GROUPS groups of 4
+// pixels, 1024 columns apart, and issues the loads of all groups before it uses any (a chunk is a chain
+// load -> stencil -> reduction -> store, and with one group per thread the kernel was bound by that
+// latency, not by bandwidth).  When the rows are 4-byte aligned a group is one word per row and the pixels
+// left / right of it come from the neighbouring lanes by shuffle.
+// Chunks are numbered row-major (slice, row, segment), so an exclusive scan of the per-chunk counts followed
+// by an in-chunk rank reproduces the row-major order of the reference's `collect()`.
 // ===========================================================================
 
-__device__ __forceinline__ uint32_t minima_mask4(const uint8_t* __restrict__ img, const ImageDims& d, int b, int r,
-                                                 int c0) {
-  // bit k set <=> pixel (r, c0+k) is an interior pixel strictly greater than its 8 neighbours
-  if (r < 1 || r > d.rows - 2) return 0u;
+// mask[g] bit k set <=> pixel (r, c0 + 1024 g + k) is an interior pixel strictly greater than its 8
+// neighbours (lib.rs:1190: all(|val| val < target_val)).  Warp-collective.
+template <bool kWords>
+__device__ __forceinline__ void minima_masks(const uint8_t* __restrict__ img, const ImageDims& d, int b, int r, int c0,
+                                             uint32_t mask[MINIMA_GROUPS]) {
+#pragma unroll
+  for (int g = 0; g < MINIMA_GROUPS; ++g) mask[g] = 0u;
+  if (r < 1 || r > d.rows - 2) return;  // (uniform: a CTA is one row segment)
   const uint8_t* base = img + (size_t)b * d.px_per_img();
-  const uint8_t* up = base + (size_t)(r - 1) * d.cols;
-  const uint8_t* mid = up + d.cols;
-  const uint8_t* dn = mid + d.cols;
-  uint32_t u[6], m[6], l[6];
+  const uint8_t* rowp[3] = {base + (size_t)(r - 1) * d.cols, base + (size_t)r * d.cols, base + (size_t)(r + 1) * d.cols};
+  uint32_t px[MINIMA_GROUPS][3][6];  // [group][row][c0-1 .. c0+4]
+  if (kWords) {
+    const int lane = threadIdx.x & 31;
+    uint32_t w[MINIMA_GROUPS][3];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const int c = c0 - 1 + k;
-    const bool in = (c >= 0 && c < d.cols);
-    u[k] = in ? __ldg(up + c) : 0u;
-    m[k] = in ? __ldg(mid + c) : 0u;
-    l[k] = in ? __ldg(dn + c) : 0u;
-  }
-  uint32_t mask = 0;
+    for (int g = 0; g < MINIMA_GROUPS; ++g) {
+      const int c = c0 + g * 1024;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = c0 + k;
-    if (c < 1 || c > d.cols - 2) continue;
-    const uint32_t t = m[k + 1];
-    // max of the 8 neighbours must be < t   (lib.rs:1190: all(|val| val < target_val))
-    uint32_t nb = max(max(u[k], u[k + 1]), u[k + 2]);
-    nb = max(nb, max(m[k], m[k + 2]));
-    nb = max(nb, max(max(l[k], l[k + 1]), l[k + 2]));
-    if (nb < t) mask |= 1u << k;
+      for (int k = 0; k < 3; ++k) w[g][k] = c < d.cols ? __ldg(reinterpret_cast<const uint32_t*>(rowp[k] + c)) : 0u;
+    }
+#pragma unroll
+    for (int g = 0; g < MINIMA_GROUPS; ++g) {
+      const int c = c0 + g * 1024;
+      const bool in = c < d.cols;  // then c + 3 < cols as well (cols % 4 == 0)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t x = w[g][k];
+        uint32_t left = __shfl_up_sync(0xffffffffu, x, 1) >> 24;
+        uint32_t right = __shfl_down_sync(0xffffffffu, x, 1) & 0xFFu;
+        if (lane == 0) left = (in && c > 0) ? __ldg(rowp[k] + c - 1) : 0u;
+        if (lane == 31) right = (in && c + 4 < d.cols) ? __ldg(rowp[k] + c + 4) : 0u;
+        px[g][k][0] = left;
+        px[g][k][1] = x & 0xFFu;
+        px[g][k][2] = (x >> 8) & 0xFFu;
+        px[g][k][3] = (x >> 16) & 0xFFu;
+        px[g][k][4] = x >> 24;
+        px[g][k][5] = right;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < MINIMA_GROUPS; ++g)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int c = c0 + g * 1024 - 1 + j;
+        const bool in = (c >= 0 && c < d.cols);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) px[g][k][j] = in ? __ldg(rowp[k] + c) : 0u;
+      }
   }
-  return mask;
+#pragma unroll
+  for (int g = 0; g < MINIMA_GROUPS; ++g)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + g * 1024 + k;
+      if (c < 1 || c > d.cols - 2) continue;
+      const uint32_t t = px[g][1][k + 1];
+      uint32_t nb = max(max(px[g][0][k], px[g][0][k + 1]), px[g][0][k + 2]);
+      nb = max(nb, max(px[g][1][k], px[g][1][k + 2]));
+      nb = max(nb, max(max(px[g][2][k], px[g][2][k + 1]), px[g][2][k + 2]));
+      if (nb < t) mask[g] |= 1u << k;
+    }
 }
 
 __device__ __forceinline__ void minima_chunk_coords(const ImageDims& d, size_t chunk, int& b, int& r, int& c0) {
@@ -63,12 +98,17 @@ __device__ __forceinline__ void minima_chunk_coords(const ImageDims& d, size_t c
   c0 = (int)(rem - (size_t)r * segs) * MINIMA_CHUNK + threadIdx.x * 4;
 }
 
+template <bool kWords>
 __global__ void __launch_bounds__(256) minima_count_kernel(const uint8_t* __restrict__ img, ImageDims d,
                                                            uint32_t* __restrict__ chunk_counts) {
   __shared__ uint32_t s_warp[8];
   int b, r, c0;
   minima_chunk_coords(d, blockIdx.x, b, r, c0);
-  uint32_t n = __popc(minima_mask4(img, d, b, r, c0));
+  uint32_t mask[MINIMA_GROUPS];
+  minima_masks<kWords>(img, d, b, r, c0, mask);
+  uint32_t n = 0;
+#pragma unroll
+  for (int g = 0; g < MINIMA_GROUPS; ++g) n += __popc(mask[g]);
 #pragma unroll
   for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = n;
@@ -132,36 +172,48 @@ __global__ void __launch_bounds__(1024) minima_scan_kernel(uint32_t* __restrict_
     seed_off[b] = (b == d.n_img) ? total[0] : v[(size_t)b * per_img];
 }
 
+template <bool kWords>
 __global__ void __launch_bounds__(256) minima_write_kernel(const uint8_t* __restrict__ img, ImageDims d,
                                                            const uint32_t* __restrict__ chunk_offsets,
                                                            uint32_t* __restrict__ out_rc, uint32_t cap) {
-  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_warp[MINIMA_GROUPS][8];
   int b, r, c0;
   minima_chunk_coords(d, blockIdx.x, b, r, c0);
-  const uint32_t mask = minima_mask4(img, d, b, r, c0);
-  const uint32_t n = __popc(mask);
-  // exclusive rank inside the CTA, in column order
-  uint32_t incl = n;
+  uint32_t mask[MINIMA_GROUPS];
+  minima_masks<kWords>(img, d, b, r, c0, mask);
+  // exclusive rank inside the chunk, in column order: group by group, inside a group thread by thread
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl[MINIMA_GROUPS];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  uint32_t pre = 0;
-  for (int w = 0; w < warp; ++w) pre += s_warp[w];
-  uint32_t pos = chunk_offsets[blockIdx.x] + pre + incl - n;
+  for (int g = 0; g < MINIMA_GROUPS; ++g) {
+    incl[g] = __popc(mask[g]);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (mask & (1u << k)) {
-      if (pos < cap) {
-        out_rc[2 * (size_t)pos] = (uint32_t)r;
-        out_rc[2 * (size_t)pos + 1] = (uint32_t)(c0 + k);
-      }
-      ++pos;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl[g], o);
+      if (lane >= o) incl[g] += t;
     }
+    if (lane == 31) s_warp[g][warp] = incl[g];
+  }
+  __syncthreads();
+  uint32_t group_base = chunk_offsets[blockIdx.x];
+#pragma unroll
+  for (int g = 0; g < MINIMA_GROUPS; ++g) {
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t x = s_warp[g][w];
+      if (w < warp) pre += x;
+      tot += x;
+    }
+    uint32_t pos = group_base + pre + incl[g] - __popc(mask[g]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (mask[g] & (1u << k)) {
+        if (pos < cap) *reinterpret_cast<uint2*>(out_rc + 2 * (size_t)pos) = make_uint2((uint32_t)r, (uint32_t)(c0 + g * 1024 + k));
+        ++pos;
+      }
+    }
+    group_base += tot;
   }
 }
 
@@ -171,7 +223,9 @@ size_t minima_num_chunks(const ImageDims& d) {
 }
 
 cudaError_t launch_minima_count(const uint8_t* img, ImageDims d, uint32_t* chunk_counts, cudaStream_t s) {
-  minima_count_kernel<<<(unsigned)minima_num_chunks(d), 256, 0, s>>>(img, d, chunk_counts);
+  const bool words = (d.cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 3u) == 0);
+  if (words) minima_count_kernel<true><<<(unsigned)minima_num_chunks(d), 256, 0, s>>>(img, d, chunk_counts);
+  else minima_count_kernel<false><<<(unsigned)minima_num_chunks(d), 256, 0, s>>>(img, d, chunk_counts);
   return cudaGetLastError();
 }
 cudaError_t launch_minima_scan(uint32_t* chunk_counts, size_t n_chunks, ImageDims d, uint32_t* seed_off,
@@ -181,7 +235,9 @@ cudaError_t launch_minima_scan(uint32_t* chunk_counts, size_t n_chunks, ImageDim
 }
 cudaError_t launch_minima_write(const uint8_t* img, ImageDims d, const uint32_t* chunk_offsets, uint32_t* out_rc,
                                 uint32_t cap, cudaStream_t s) {
-  minima_write_kernel<<<(unsigned)minima_num_chunks(d), 256, 0, s>>>(img, d, chunk_offsets, out_rc, cap);
+  const bool words = (d.cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 3u) == 0);
+  if (words) minima_write_kernel<true><<<(unsigned)minima_num_chunks(d), 256, 0, s>>>(img, d, chunk_offsets, out_rc, cap);
+  else minima_write_kernel<false><<<(unsigned)minima_num_chunks(d), 256, 0, s>>>(img, d, chunk_offsets, out_rc, cap);
   return cudaGetLastError();
 }
 

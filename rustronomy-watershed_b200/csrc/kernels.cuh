@@ -53,7 +53,8 @@ int jump_max_grid(int device);
 int union_max_grid(int device);
 
 // --- seeds (find_local_minima, lib.rs:1178-1197) ---------------------------
-constexpr int MINIMA_CHUNK = 1024;  // columns per chunk (one CTA of 256 threads x 4 px)
+constexpr int MINIMA_GROUPS = 4;     // every thread handles 4 groups of 4 pixels, 1024 columns apart
+constexpr int MINIMA_CHUNK = 1024 * MINIMA_GROUPS;  // columns per chunk (one CTA of 256 threads)
 size_t minima_num_chunks(const ImageDims& d);
 cudaError_t launch_minima_count(const uint8_t* img, ImageDims d, uint32_t* chunk_counts, cudaStream_t s);
 // exclusive scan in place; writes seed_off[n_img+1] and total[0]
