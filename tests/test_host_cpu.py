@@ -95,3 +95,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "ws_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the oracle on the host cores) needs no GPU: one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-crop", "96", "--size", "256"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["value"] > 0
+    for key in ("metric", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config", "cpu_baseline", "e2e"):
+        assert key in d
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
