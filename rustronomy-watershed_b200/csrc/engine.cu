@@ -407,7 +407,7 @@ static ws_status plan_merge(ws_plan* p) {
 #endif
   WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, 0, p->seed_off, p->d.n_img,
                                p->mb.level_hist, p->mb.level_cursor, p->mb.fin_hist, p->mb.edges, s));
-  WS_CUDA(ctx, launch_uf_init(p->mb, p->fb.lab, p->d, p->seeds, p->seed_off, (uint32_t)p->nseeds, s));
+  WS_CUDA(ctx, launch_uf_init(p->mb, p->d, (uint32_t)p->nseeds, s));
   WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
   WS_CUDA(ctx, launch_lake_counts(p->mb, p->d.n_img, lmax, s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
@@ -427,7 +427,7 @@ static ws_status plan_build_tree(ws_plan* p) {
   const uint32_t lmax = p->cfg.max_water_level;
   WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, 1, p->seed_off, p->d.n_img,
                                p->mb.level_hist, p->mb.level_cursor, p->mb.fin_hist, p->mb.edges, s));
-  WS_CUDA(ctx, launch_uf_init(p->mb, p->fb.lab, p->d, p->seeds, p->seed_off, (uint32_t)p->nseeds, s));
+  WS_CUDA(ctx, launch_uf_init(p->mb, p->d, (uint32_t)p->nseeds, s));
   WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
   p->stats[4] += 6;
   p->tree_built = true;
@@ -463,7 +463,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   p->bucket_shift = flood_bucket_shift(nseeds_total, p->d);
   WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
-  WS_CUDA(ctx, launch_parent(p->fb, p->d, s));
+  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, s));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[3], s));
   p->stats[4] += 4 + (nseeds_total ? 1 : 0);
@@ -685,7 +685,7 @@ extern "C" ws_status ws_plan_strip_labels(ws_plan* p) {
   if (!p) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
-  WS_CUDA(ctx, launch_parent(p->fb, p->d, ctx->stream));
+  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, ctx->stream));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, ctx->stream));
   p->stats[4] += 2;
   WS_TRY(check_flood_errors(p));
@@ -1187,24 +1187,11 @@ extern "C" ws_status ws_transform_lake_counts(ws_ctx* ctx, const ws_config* cfg,
   WS_CUDA(ctx, cudaStreamSynchronize(s));
   p->stats[4] += 1;
   if (cfg->kind == WS_SEGMENTING) {
-    // no merges: every colour present on the canvas is a lake at every level
+    // no merges: every colour present on the canvas (counted by label_tile) is a lake at every level
     std::vector<uint32_t> nd(1);
-    MergeBuffers& m = p->mb;
-    // count distinct colours with the same kernel the merging path uses
-    if (p->nseeds > p->uf_cap || !m.parent) {
-      cudaFree(m.parent); cudaFree(m.hook_to); cudaFree(m.hook_lvl);
-      m.parent = m.hook_to = nullptr; m.hook_lvl = nullptr; p->uf_cap = 0;
-      const size_t n = std::max<size_t>(p->nseeds, 1);
-      WS_CUDA(ctx, cudaMalloc((void**)&m.parent, n * 4));
-      WS_CUDA(ctx, cudaMalloc((void**)&m.hook_to, n * 4));
-      WS_CUDA(ctx, cudaMalloc((void**)&m.hook_lvl, n));
-      p->uf_cap = n;
-    }
-    WS_CUDA(ctx, launch_uf_init(m, p->fb.lab, p->d, p->seeds, p->seed_off, (uint32_t)p->nseeds, s));
-    WS_CUDA(ctx, cudaMemcpyAsync(nd.data(), m.ndistinct, 4, cudaMemcpyDeviceToHost, s));
+    WS_CUDA(ctx, cudaMemcpyAsync(nd.data(), p->mb.ndistinct, 4, cudaMemcpyDeviceToHost, s));
     WS_CUDA(ctx, cudaStreamSynchronize(s));
     for (uint32_t l = 0; l < nlev; ++l) h_counts[l] = nd[0];
-    p->stats[4] += 1;
   }
   uint64_t coloured = 0;
   for (uint32_t l = 0; l < nlev; ++l) {

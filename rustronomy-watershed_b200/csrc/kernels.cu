@@ -257,41 +257,13 @@ static int coop_max_grid(const void* fn, int threads, int device) {
 //     (find_merge / make_colour_map / recolour, lib.rs:393-542, 590-592)
 // ===========================================================================
 
-// union-find initialisation + number of colours actually present on the canvas
-// (a seed position overwritten by a later duplicate seed loses its colour, lib.rs:1365-1367)
-__global__ void __launch_bounds__(256) uf_init_kernel(MergeBuffers m, const uint32_t* __restrict__ lab,
-                                                      ImageDims d, const uint32_t* __restrict__ seeds_rc,
-                                                      const uint32_t* __restrict__ seed_off, uint32_t nseeds) {
+// union-find initialisation (the number of colours present on the canvas comes from label_tile)
+__global__ void __launch_bounds__(256) uf_init_kernel(MergeBuffers m, uint32_t nseeds) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  int lo = 0;
-  bool present = false;
-  if (i < nseeds) {
-    m.parent[i] = i;
-    m.hook_to[i] = i;
-    m.hook_lvl[i] = 255;
-    int hi = d.n_img;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
-    }
-    const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
-    if (r < (uint32_t)d.rows && c < (uint32_t)d.cols) {
-      const size_t p = (size_t)lo * d.px_per_img() + (size_t)r * d.cols + c;
-      present = (lab[p] & LAB_MASK) == i - __ldg(seed_off + lo) + 1u;
-    }
-  }
-  // one atomic per CTA when the whole CTA lies in one slice (seeds are grouped by slice)
-  __shared__ int s_lo[2];
-  if (threadIdx.x == 0) s_lo[0] = lo;
-  if (i == nseeds - 1 || (threadIdx.x == blockDim.x - 1 && i < nseeds)) s_lo[1] = lo;
-  __syncthreads();
-  const bool uniform = (s_lo[0] == s_lo[1]);
-  const int n = __syncthreads_count(present && uniform);
-  if (uniform) {
-    if (threadIdx.x == 0 && n) atomicAdd(&m.ndistinct[s_lo[0]], (uint32_t)n);
-  } else if (present) {
-    atomicAdd(&m.ndistinct[lo], 1u);
-  }
+  if (i >= nseeds) return;
+  m.parent[i] = i;
+  m.hook_to[i] = i;
+  m.hook_lvl[i] = 255;
 }
 
 // strips: union-find over GLOBAL colours, reset only (the number of colours present comes from the host)
@@ -331,13 +303,10 @@ cudaError_t launch_count_present(const uint32_t* lab, ImageDims d, const uint32_
   return cudaGetLastError();
 }
 
-cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,
-                           const uint32_t* seed_off, uint32_t nseeds, cudaStream_t s) {
+cudaError_t launch_uf_init(MergeBuffers m, ImageDims d, uint32_t nseeds, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(m.unions, 0, sizeof(uint32_t) * 256 * (size_t)d.n_img, s);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(m.ndistinct, 0, sizeof(uint32_t) * (size_t)d.n_img, s);
   if (e != cudaSuccess || nseeds == 0) return e;
-  uf_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(m, lab, d, seeds_rc, seed_off, nseeds);
+  uf_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(m, nseeds);
   return cudaGetLastError();
 }
 

@@ -90,7 +90,8 @@ cudaError_t launch_unpad_T(const uint32_t* Tp, ImageDims d, uint32_t* out, cudaS
 
 // --- labels (colour decision of lib.rs:235-255 with the `col0` tie-break) ---
 size_t rim_words(const ImageDims& d);
-cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s);
+// also counts, per slice, the owned pixels that hold a seed = colours present on the canvas (ndistinct[n_img])
+cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, cudaStream_t s);
 cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s);
 
 // --- merging (find_merge + make_colour_map + recolour, lib.rs:393-542, 590-592) ---
@@ -106,7 +107,7 @@ struct MergeBuffers {
   uint8_t* hook_lvl;      // [nseeds] level of that link, 255 = still a root
   uint32_t* unions;       // [n_img][256] successful unions per level
   uint32_t* fin_hist;     // [n_img][256] FINAL forest edges per level (contracted in their tile, never unioned globally)
-  uint32_t* ndistinct;    // [n_img] colours present on the canvas
+  uint32_t* ndistinct;    // [n_img] colours present on the canvas (counted by label_tile)
   uint32_t* counts;       // [n_img][256] lakes per level
 };
 // per-tile contraction + spanning-forest reduction in shared memory (merge.cu).  Edges: .x / .y = global
@@ -119,8 +120,7 @@ cudaError_t launch_merge_reduce(const uint32_t* lab, const uint8_t* lvl, ImageDi
 cudaError_t launch_red_sort(const uint2* red_ab, const uint8_t* red_w, const uint32_t* red_count, int all,
                             const uint32_t* seed_off, int n_img, uint32_t* level_hist, uint32_t* level_cursor,
                             uint32_t* fin_hist, uint2* edges, cudaStream_t s);
-cudaError_t launch_uf_init(MergeBuffers m, const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc,
-                           const uint32_t* seed_off, uint32_t nseeds, cudaStream_t s);
+cudaError_t launch_uf_init(MergeBuffers m, ImageDims d, uint32_t nseeds, cudaStream_t s);
 cudaError_t launch_uf_reset(MergeBuffers m, uint32_t n, cudaStream_t s);
 cudaError_t launch_count_present(const uint32_t* lab, ImageDims d, const uint32_t* seeds_rc, uint32_t nseeds,
                                  uint32_t colour_base, uint32_t* out, cudaStream_t s);

@@ -50,9 +50,11 @@ struct __align__(128) LabelSmem {
   uint32_t T[LT_H * LT_W];
   uint32_t w[TILE_H * TILE_W];     // per pixel: LT_LOCAL | next pixel inside the tile, or its final word
   uint64_t bar;
+  uint32_t nseed_px;
 };
 
-__global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, ImageDims d) {
+__global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, ImageDims d,
+                                                                uint32_t* __restrict__ ndistinct) {
   __shared__ LabelSmem sm;
   const int tid = threadIdx.x;
   const int tpi = d.tiles_per_img();
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   // launch, so no cross-proxy fence is needed here
   const uint32_t* tsrc = b.T + (size_t)img * d.t_plane() + (size_t)r0 * tp + c0;
   if (tid == 0) {
+    sm.nseed_px = 0;
     mbar_init(&sm.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_arrive_expect_tx(&sm.bar, LT_H * LT_W * 4);
@@ -77,6 +80,7 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   const int lc = tid % TILE_W, g = tid / TILE_W;
   const size_t base = (size_t)img * d.px_per_img();
   const uint32_t rim_total = (uint32_t)d.tiles_total() * RIM_PER_TILE;
+  int nseed_px = 0;  // owned pixels that hold a seed (arrival time 0): the colours present on the canvas
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     const int lr = g * ROWS_PER_THREAD + i;
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
         b.rim[term] = term;
       } else if (tv == 0u) {
         term = __ldcg(b.lab + p);  // seed: coloured by seed_init
+        ++nseed_px;
       } else {
         // A coloured non-seed pixel is interior, so all four neighbours exist.
         int dr = 0, dc = 0;
@@ -118,7 +123,14 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
     }
     sm.w[li] = term;
   }
+  {
+    // (a later duplicate seed overwrites an earlier one, lib.rs:1365-1367, so a pixel counts once)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nseed_px += __shfl_xor_sync(0xffffffffu, nseed_px, o);
+    if ((tid & 31) == 0 && nseed_px) atomicAdd(&sm.nseed_px, (uint32_t)nseed_px);
+  }
   __syncthreads();
+  if (tid == 0 && sm.nseed_px) atomicAdd(&ndistinct[img], sm.nseed_px);  // one global atomic per tile
 
   // pointer jumping inside the tile (reads and writes separated by barriers); `act` = my pixels that
   // still hold an in-tile pointer
@@ -159,8 +171,10 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   }
 }
 
-cudaError_t launch_parent(FloodBuffers b, ImageDims d, cudaStream_t s) {
-  label_tile_kernel<<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d);
+cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(ndistinct, 0, sizeof(uint32_t) * (size_t)d.n_img, s);
+  if (e != cudaSuccess) return e;
+  label_tile_kernel<<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d, ndistinct);
   return cudaGetLastError();
 }
 
