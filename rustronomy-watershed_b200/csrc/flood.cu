@@ -12,12 +12,14 @@
 //     re-ran every tile ~9-12 times on smooth fields; this order needs ~4).  The flood ends when the
 //     count of queued + in-flight entries reaches zero;
 //   * every CTA = 8 consumer warps + 1 producer warp.  The producer claims tiles, stages each tile's
-//     34 x 72-word box of arrival times and its 32 x 64 image bytes with the bulk-copy engine
-//     (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) into a two-stage ring, and afterwards
-//     publishes the tile's neighbours to the worklist.  The consumers never wait on a global round
-//     trip: they copy the stage into an odd-stride working tile and iterate on it;
+//     34 x 72-word box of arrival times and its 32 x 64 image bytes with two 2-D tensor copies
+//     (cp.async.bulk.tensor.2d -> SASS UTMALDG, completion on an mbarrier) into a two-stage ring, and
+//     publishes a finished tile's neighbours to the worklist after the stage has been refilled.  The
+//     consumers never wait on a global round trip: they copy the stage into an odd-stride working tile
+//     and iterate on it;
 //   * the in-tile iteration alternates column and row ownership (8 pixels of Gauss-Seidel
-//     along the phase's axis per step) until a phase changes nothing;
+//     along the phase's axis per step) until a phase changes nothing; a warp skips a phase when
+//     neither its cells nor the cells next to them changed in the previous one;
 //   * results go back with atomicMin: two CTAs may (rarely) hold the same tile at once, and arrival
 //     times must never go up.
 #include "kernels.cuh"
