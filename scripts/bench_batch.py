@@ -6,7 +6,8 @@ data-parallel over the GPUs of one box (one process per GPU, no data-path collec
         [--slices 1024] [--chunk 64] [--reps 2]
 
 Every rank takes slices/N slices and runs them in chunks of `chunk` slices (one device plan per chunk
-shape, reused).  Per chunk, inside the timed region: H2D of the slices from pinned host memory, seed
+shape, reused).  Per chunk, inside the timed region: H2D of the slices from pinned host memory (double
+buffered on a copy stream, so that chunk k + 1 crosses the link while chunk k is in the kernels), seed
 finding on the device, the segmenting run, the merging run, D2H of the per-slice lake counts.  Rank 0
 prints one JSON line: total time = max over ranks; device_ms = the kernels alone (CUDA events).
 """
@@ -50,43 +51,61 @@ def main():
     base = np.stack([fieldgen.cgps_like(S, S, seed=rank * args.distinct + i) for i in range(args.distinct)])
     host = torch.from_numpy(np.concatenate([base] * ((chunk + args.distinct - 1) // args.distinct))[:chunk]).pin_memory()
     plan = ws.Plan(ctx, chunk, S, S)
-    d_img = torch.empty((chunk, S, S), dtype=torch.uint8, device="cuda")
+    d_img = [torch.empty((chunk, S, S), dtype=torch.uint8, device="cuda") for _ in range(2)]  # double buffer
     d_off = torch.zeros(chunk + 1, dtype=torch.int32, device="cuda")
     cap = int(0.12 * chunk * S * S)
     d_seeds = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
     counts_h = torch.empty((chunk, 256), dtype=torch.int32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=local)
+    ready = [torch.cuda.Event() for _ in range(2)]     # slices of buffer b are on the device
+    done = [torch.cuda.Event() for _ in range(2)]      # the kernels have finished with buffer b
 
     class _Dev:
         def __init__(self, ptr, shape):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": "<i4", "data": (int(ptr), False), "version": 2}
 
-    def one_chunk():
-        with torch.cuda.stream(stream):
-            d_img.copy_(host, non_blocking=True)
-        stream.synchronize()
+    def upload(b):
+        """H2D of the next chunk on the copy stream: overlaps the kernels of the current one."""
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[b])
+            d_img[b].copy_(host, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def compute(b):
+        stream.wait_event(ready[b])
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        n = plan.find_local_minima(d_img.data_ptr(), d_seeds.data_ptr(), cap, d_off.data_ptr())
-        plan.run(0, 254, d_img.data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), n)
-        plan.run(1, 254, d_img.data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), n)
+        n = plan.find_local_minima(d_img[b].data_ptr(), d_seeds.data_ptr(), cap, d_off.data_ptr())
+        plan.run(0, 254, d_img[b].data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), n)
+        plan.run(1, 254, d_img[b].data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), n)
         e1.record(stream)
+        done[b].record(stream)
         with torch.cuda.stream(stream):
             counts_h.copy_(torch.as_tensor(_Dev(plan.lake_counts_ptr, (chunk, 256)), device="cuda"), non_blocking=True)
         stream.synchronize()
         return n, e0.elapsed_time(e1)
 
-    one_chunk()  # warm-up
+    def run_all():
+        dev_ms, seeds = 0.0, 0
+        upload(0)
+        for c in range(nchunks):
+            if c + 1 < nchunks:
+                upload((c + 1) & 1)
+            n, ms = compute(c & 1)
+            dev_ms += ms
+            seeds += n
+        return dev_ms, seeds
+
+    for b in range(2):
+        done[b].record(stream)
+    run_all()  # warm-up
     best = None
     for _ in range(args.reps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        dev_ms, seeds = 0.0, 0
-        for _c in range(nchunks):
-            n, ms = one_chunk()
-            dev_ms += ms
-            seeds += n
+        dev_ms, seeds = run_all()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         t = torch.tensor([wall, dev_ms], device="cuda", dtype=torch.float64)
