@@ -223,6 +223,10 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
         sm.b.r.comp[i] = (uint16_t)(x | ((sm.flags[x] & 1) ? OPEN : 0u));
       }
       __syncthreads();
+#ifdef WS_MERGE_STATS  // rounds and edge looks per stage (scripts/merge_stats.py)
+      if (tid == 0) atomicAdd(&red_count[4 + stage], 1u);
+      if (lane == 0) atomicAdd(&red_count[6 + stage], cnt);
+#endif
       // one pass over my warp's live edges: drop those inside one component, keep the rest compacted,
       // offer each to the components at its ends
       bool any = false;

@@ -1,4 +1,7 @@
-"""Per-tile statistics of merge_reduce (needs a library built with -DWS_MERGE_STATS; diagnostic)."""
+"""Per-tile statistics of merge_reduce (diagnostic).  Needs a library built with -DWS_MERGE_STATS, e.g.
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared -DWS_MERGE_STATS \\
+         -o scripts/libws_stats.so rustronomy-watershed_b200/csrc/{kernels,flood,labels,merge,engine}.cu
+    WS_B200_LIB=scripts/libws_stats.so python scripts/merge_stats.py 8192 uniform"""
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 import fieldgen
