@@ -61,11 +61,20 @@ typedef enum ws_kind {
 } ws_kind;
 
 /* The fields of TransformBuilder that reach the hot path (lib.rs:917-919).    */
+/* Colour of a pixel whose coloured neighbours disagree (lib.rs:246-254).  The reference draws one of the
+ * coloured 4-neighbours uniformly with thread_rng(); WS_TIE_FIRST (the default) takes the first of them
+ * in the reference's neighbour order down, right, left, up (`col0`, lib.rs:190, 245) -- always one of the
+ * reference's possible outcomes, and reproducible.  WS_TIE_RANDOM draws like the reference (uniform over
+ * the coloured neighbours, multiplicity included) from a counter-based generator keyed by
+ * ws_ctx_set_tie_seed() and the pixel's position, so a given seed reproduces the image.  Merging results
+ * (partitions, lake counts, sizes) do not depend on the tie-break.                                      */
+typedef enum ws_tie_break { WS_TIE_FIRST = 0, WS_TIE_RANDOM = 1 } ws_tie_break;
+
 typedef struct ws_config {
   uint8_t kind;            /* ws_kind                                          */
   uint8_t max_water_level; /* 1..=254, default NORMAL_MAX (lib.rs:942)         */
   uint8_t edge_correction; /* enable_edge_correction(), lib.rs:958-961         */
-  uint8_t reserved;        /* must be 0                                        */
+  uint8_t tie_break;       /* ws_tie_break (was `reserved`, 0 = WS_TIE_FIRST)  */
 } ws_config;
 
 /* ArrayView2<u8>: base pointer of element (0,0), shape, strides in elements.  */
@@ -86,6 +95,8 @@ const char *ws_status_str(ws_status s);
 int ws_abi_version(void);
 /* Frees memory handed out by the library (ws_find_local_minima).              */
 void ws_free(void *p);
+/* Key of the WS_TIE_RANDOM generator (default: drawn from the OS when the ctx is made, like thread_rng). */
+ws_status ws_ctx_set_tie_seed(ws_ctx *ctx, uint64_t seed);
 
 /* ---- TransformBuilder::build_segmenting / build_merging (lib.rs:998-1046) -- */
 /* Only the validation is left to do: 1 <= max_water_level <= 254.             */
@@ -179,6 +190,15 @@ ws_status ws_transform_lake_counts(ws_ctx *ctx, const ws_config *cfg,
                                    const ws_image *img, const uint64_t *seeds_rc,
                                    size_t nseeds, uint64_t *out_lake_counts,
                                    uint64_t *out_uncoloured);
+/* Per level the lake sizes without the (rows*cols+1)-long rows of transform_to_list: out_sizes is
+ * [max+1][nseeds+1] uint64, column 0 = uncoloured pixels, column c = pixels of colour c (a merged lake is
+ * held by its representative, the other columns of the lake are 0) -- the first nseeds+1 entries of every
+ * find_lake_sizes row (lib.rs:629-635); the rest of those rows is zero by construction.
+ * out_lake_counts (optional): max+1 uint64, number of non-empty lakes per level.                        */
+ws_status ws_transform_lake_sizes_compact(ws_ctx *ctx, const ws_config *cfg,
+                                          const ws_image *img, const uint64_t *seeds_rc,
+                                          size_t nseeds, uint64_t *out_lake_counts,
+                                          uint64_t *out_sizes);
 /* Final segmenting labels as uint32 plus, per pixel, the water level at which
  * it was coloured (255 = never): snapshot L == (level <= L ? label : 0).      */
 ws_status ws_transform_compact(ws_ctx *ctx, const ws_config *cfg,

@@ -22,11 +22,12 @@ STATUS_NAMES = {
 }
 WS_ERR_MAX_TOO_HIGH, WS_ERR_MAX_TOO_LOW, WS_ERR_SEED_OOB, WS_ERR_NO_DEVICE = 2, 3, 4, 5
 WS_SEGMENTING, WS_MERGING = 0, 1
+WS_TIE_FIRST, WS_TIE_RANDOM = 0, 1
 
 
 class WsConfig(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("max_water_level", C.c_uint8),
-                ("edge_correction", C.c_uint8), ("reserved", C.c_uint8)]
+                ("edge_correction", C.c_uint8), ("tie_break", C.c_uint8)]
 
 
 class WsImage(C.Structure):
@@ -57,6 +58,7 @@ SIGNATURES = {
     "ws_status_str": (C.c_char_p, [C.c_int]),
     "ws_abi_version": (C.c_int, []),
     "ws_free": (None, [_P]),
+    "ws_ctx_set_tie_seed": (C.c_int, [_P, C.c_uint64]),
     "ws_config_validate": (C.c_int, [C.POINTER(WsConfig)]),
     "ws_output_shape": (C.c_int, [C.POINTER(WsConfig), C.c_size_t, C.c_size_t,
                                   C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -67,6 +69,8 @@ SIGNATURES = {
     "ws_transform_with_hook": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t,
                                          HOOK_FN, _P]),
     "ws_transform_lake_counts": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t, _P, _P]),
+    "ws_transform_lake_sizes_compact": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t,
+                                                  _P, _P]),
     "ws_transform_compact": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsImage), _P, C.c_size_t, _P, _P]),
     "ws_transform_batch": (C.c_int, [_P, C.POINTER(WsConfig), _P, C.c_size_t, C.c_size_t, C.c_size_t,
                                      _P, _P, _P, _P]),
@@ -133,8 +137,8 @@ def load_library(path: Optional[str] = None):
     return lib
 
 
-def make_config(kind: int, max_water_level: int, edge_correction: bool) -> WsConfig:
-    return WsConfig(kind, max_water_level, 1 if edge_correction else 0, 0)
+def make_config(kind: int, max_water_level: int, edge_correction: bool, tie_break: int = WS_TIE_FIRST) -> WsConfig:
+    return WsConfig(kind, max_water_level, 1 if edge_correction else 0, tie_break)
 
 
 def image_view(img: np.ndarray) -> WsImage:
@@ -210,6 +214,10 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.ws_ctx_synchronize(self.handle))
+
+    def set_tie_seed(self, seed: int):
+        """Key of the WS_TIE_RANDOM generator (default: drawn from the OS per context, like thread_rng)."""
+        self.check(self.lib.ws_ctx_set_tie_seed(self.handle, int(seed) & 0xFFFFFFFFFFFFFFFF))
 
 
 _default_ctx = {}

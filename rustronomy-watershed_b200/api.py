@@ -69,6 +69,8 @@ class TransformBuilder(Generic[T]):
         self.edge_correction = False
         self.wlvl_hook: Optional[Callable[[HookCtx], T]] = None
         self.device = 0
+        self.tie_break = N.WS_TIE_FIRST
+        self.tie_seed: Optional[int] = None
 
     @classmethod
     def new(cls) -> "TransformBuilder":
@@ -97,8 +99,15 @@ class TransformBuilder(Generic[T]):
         self.device = int(device)
         return self
 
+    def set_tie_break(self, policy: str, seed: Optional[int] = None) -> "TransformBuilder":
+        """Extension: "first" (default; the reference's `col0`, lib.rs:245) or "random" (the reference's own
+        behaviour, lib.rs:250-253: uniform over the coloured neighbours; `seed` makes it reproducible)."""
+        self.tie_break = {"first": N.WS_TIE_FIRST, "random": N.WS_TIE_RANDOM}[policy]
+        self.tie_seed = seed
+        return self
+
     def _validate(self, kind: int):
-        cfg = N.make_config(kind, self.max_water_level, self.edge_correction)
+        cfg = N.make_config(kind, self.max_water_level, self.edge_correction, self.tie_break)
         st = N.load_library().ws_config_validate(C.byref(cfg))
         if st == N.WS_ERR_MAX_TOO_HIGH:
             raise BuildErr.MaxToHigh(self.max_water_level)      # lib.rs:1000-1001
@@ -109,11 +118,13 @@ class TransformBuilder(Generic[T]):
 
     def build_merging(self) -> "MergingWatershed":
         self._validate(N.WS_MERGING)
-        return MergingWatershed(self.max_water_level, self.edge_correction, self.wlvl_hook, self.device)
+        return MergingWatershed(self.max_water_level, self.edge_correction, self.wlvl_hook, self.device,
+                                self.tie_break, self.tie_seed)
 
     def build_segmenting(self) -> "SegmentingWatershed":
         self._validate(N.WS_SEGMENTING)
-        return SegmentingWatershed(self.max_water_level, self.edge_correction, self.wlvl_hook, self.device)
+        return SegmentingWatershed(self.max_water_level, self.edge_correction, self.wlvl_hook, self.device,
+                                   self.tie_break, self.tie_seed)
 
 
 class WatershedUtils:
@@ -170,15 +181,20 @@ class Watershed(WatershedUtils, Generic[T]):
     KIND = N.WS_SEGMENTING
 
     def __init__(self, max_water_level: int, edge_correction: bool,
-                 wlvl_hook: Optional[Callable[[HookCtx], T]], device: int = 0):
+                 wlvl_hook: Optional[Callable[[HookCtx], T]], device: int = 0,
+                 tie_break: int = N.WS_TIE_FIRST, tie_seed: Optional[int] = None):
         self.max_water_level = max_water_level
         self.edge_correction = edge_correction
         self.wlvl_hook = wlvl_hook
         self.device = device
+        self.tie_break = tie_break
+        self.tie_seed = tie_seed
 
     # -- helpers --------------------------------------------------------------
     def _cfg(self) -> N.WsConfig:
-        return N.make_config(self.KIND, self.max_water_level, self.edge_correction)
+        if self.tie_break == N.WS_TIE_RANDOM and self.tie_seed is not None:
+            self._ctx().set_tie_seed(self.tie_seed)
+        return N.make_config(self.KIND, self.max_water_level, self.edge_correction, self.tie_break)
 
     def _out_shape(self, img: np.ndarray) -> Tuple[int, int]:
         pad = 2 if self.edge_correction else 0            # lib.rs:1330-1336
@@ -261,6 +277,17 @@ class Watershed(WatershedUtils, Generic[T]):
                                                    s.shape[0], lakes.ctypes.data, unc.ctypes.data))
         return lakes, unc
 
+    def lake_sizes_compact(self, input: np.ndarray, seeds: Sequence) -> Tuple[np.ndarray, np.ndarray]:
+        """(lakes per level [levels], sizes [levels][nseeds+1]): the first nseeds+1 entries of every
+        find_lake_sizes row of transform_to_list (the rest of those rows is zero)."""
+        ctx = self._ctx()
+        cfg, view, s = self._cfg(), N.image_view(input), N.seeds_array(seeds)
+        lakes = np.empty(self.levels, dtype=np.uint64)
+        sizes = np.empty((self.levels, s.shape[0] + 1), dtype=np.uint64)
+        ctx.check(ctx.lib.ws_transform_lake_sizes_compact(ctx.handle, C.byref(cfg), C.byref(view), s.ctypes.data,
+                                                          s.shape[0], lakes.ctypes.data, sizes.ctypes.data))
+        return lakes, sizes
+
     def transform_compact(self, input: np.ndarray, seeds: Sequence) -> Tuple[np.ndarray, np.ndarray]:
         """(uint32 final segmenting labels, uint8 level of colouring; 255 = never)."""
         ctx = self._ctx()
@@ -297,7 +324,9 @@ class Watershed(WatershedUtils, Generic[T]):
         a = np.ascontiguousarray(imgs, dtype=np.uint8)
         assert a.ndim == 3
         cfg, s = self._cfg(), N.seeds_array(seeds)
-        off = np.ascontiguousarray(seed_offsets, dtype=np.uint64)
+        off = np.ascontiguousarray(seed_offsets, dtype=np.uint64).ravel()
+        if off.shape[0] != a.shape[0] + 1 or int(off[0]) != 0 or int(off[-1]) != s.shape[0] or np.any(np.diff(off.astype(np.int64)) < 0):
+            raise ValueError("seed_offsets must have n_img + 1 ascending entries, starting at 0 and ending at len(seeds)")
         pad = 2 if self.edge_correction else 0
         labels = np.empty((a.shape[0], a.shape[1] + pad, a.shape[2] + pad), dtype=np.uint64) if want_labels else None
         counts = np.empty((a.shape[0], self.levels), dtype=np.uint64) if want_lake_counts else None

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <random>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,6 +33,7 @@ struct ws_ctx {
   cudaStream_t copy_stream = nullptr;
   int flood_grid = 0, jump_grid = 0, union_grid = 0;
   std::string err;
+  uint64_t tie_seed = 0;      // key of the WS_TIE_RANDOM generator
   ws_plan* cached = nullptr;  // workspace reused by the host-level entry points
   // host-level scratch (device)
   uint8_t* d_img = nullptr;   size_t d_img_cap = 0;
@@ -58,6 +60,7 @@ struct ws_plan {
   uint32_t* d_strip_off = nullptr;   // [2] seed offsets {0, nseeds} of a strip run
   uint32_t colour_base = 0;          // strips: colour of local seed i = colour_base + i + 1
   int bucket_shift = 2;              // priority granularity of the flood's worklist in the last run
+  int check_ovf = 0;                 // hop counters can overflow: the (whole) field has more than 2^24 pixels
   alignas(64) unsigned char tmaps[FLOOD_TENSOR_MAP_BYTES];  // tensor maps of fb.T / fb.pix for the flood's tile copies
   uint2* union_edges = nullptr;      // ws_plan_union_edges: the gathered edges bucketed by level
   size_t union_edges_cap = 0;
@@ -165,7 +168,7 @@ extern "C" ws_status ws_config_validate(const ws_config* cfg) {
   if (cfg->kind != WS_SEGMENTING && cfg->kind != WS_MERGING) return WS_ERR_INVALID_ARG;
   if (cfg->max_water_level > WS_NORMAL_MAX) return WS_ERR_MAX_TOO_HIGH;   // lib.rs:1000 / 1026
   if (cfg->max_water_level <= WS_ALWAYS_FILL) return WS_ERR_MAX_TOO_LOW;  // lib.rs:1002 / 1028
-  if (cfg->reserved != 0) return WS_ERR_INVALID_ARG;
+  if (cfg->tie_break != WS_TIE_FIRST && cfg->tie_break != WS_TIE_RANDOM) return WS_ERR_INVALID_ARG;
   return WS_OK;
 }
 
@@ -198,6 +201,10 @@ extern "C" ws_status ws_ctx_create(int device, ws_ctx** out) {
   ws_ctx* c = new (std::nothrow) ws_ctx();
   if (!c) return WS_ERR_INTERNAL;
   c->device = device;
+  {  // like thread_rng(): seeded from the OS, different for every context unless the caller sets it
+    std::random_device rd;
+    c->tie_seed = ((uint64_t)rd() << 32) ^ (uint64_t)rd() ^ (uint64_t)(uintptr_t)c;
+  }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
@@ -240,6 +247,12 @@ extern "C" void ws_ctx_destroy(ws_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
+}
+
+extern "C" ws_status ws_ctx_set_tie_seed(ws_ctx* ctx, uint64_t seed) {
+  if (!ctx) return WS_ERR_INVALID_ARG;
+  ctx->tie_seed = seed;
+  return WS_OK;
 }
 
 extern "C" void* ws_ctx_stream(ws_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -455,7 +468,8 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   for (auto& v : p->stats) v = 0;
 
   // hop counters can only overflow when a single slice has more than 2^24 pixels
-  const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
+  p->check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
+  const int check_ovf = p->check_ovf;
   WS_CUDA(ctx, cudaEventRecord(p->ev[0], s));
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_imgs, cfg->max_water_level, s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, 0u, s));
@@ -463,7 +477,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   p->bucket_shift = flood_bucket_shift(nseeds_total, p->d);
   WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
-  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, s));
+  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, cfg->tie_break == WS_TIE_RANDOM, ctx->tie_seed, s));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[3], s));
   p->stats[4] += 4 + (nseeds_total ? 1 : 0);
@@ -492,6 +506,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
     return fail(ctx, WS_ERR_INTERNAL, msg);
   }
   if (err & 16u) return fail(ctx, WS_ERR_INTERNAL, "flood worklist watchdog fired");
+  if (err & 32u) return fail(ctx, WS_ERR_INTERNAL, "flood worklist: a ring slot was overwritten while in use");
   p->ran = true;
   return WS_OK;
 }
@@ -607,6 +622,7 @@ ws_status check_flood_errors(ws_plan* p) {
     return fail(ctx, WS_ERR_INTERNAL, msg);
   }
   if (err & 16u) return fail(ctx, WS_ERR_INTERNAL, "flood worklist watchdog fired");
+  if (err & 32u) return fail(ctx, WS_ERR_INTERNAL, "flood worklist: a ring slot was overwritten while in use");
   return WS_OK;
 }
 int first_owned(const ws_plan* p) { return p->d.halo_top ? 1 : 0; }
@@ -641,11 +657,12 @@ extern "C" ws_status ws_plan_strip_begin(ws_plan* p, const ws_config* cfg, const
   p->h_ctrl[FC_WORDS + 2] = 0;
   p->h_ctrl[FC_WORDS + 3] = (uint32_t)nseeds;
   WS_CUDA(ctx, cudaMemcpyAsync(p->d_strip_off, p->h_ctrl + FC_WORDS + 2, 8, cudaMemcpyHostToDevice, s));
-  const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
+  // hop counters cross strip boundaries through the halo exchange: the WHOLE field decides
+  p->check_ovf = (size_t)st->global_rows * (size_t)p->d.cols > (size_t)HOP_MASK ? 1 : 0;
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_img, cfg->max_water_level, s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, p->d_strip_off, (uint32_t)nseeds, st->colour_base, s));
   p->bucket_shift = flood_bucket_shift(nseeds, p->d);
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, p->check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   p->stats[4] += 3;
   return check_flood_errors(p);
 }
@@ -673,8 +690,7 @@ extern "C" ws_status ws_plan_strip_import_times(ws_plan* p, const uint32_t* d_to
   if (d_top && p->d.halo_top) WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, 0, 1, d_top, p->bucket_shift, s));
   if (d_bottom && p->d.halo_bottom)
     WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, p->d.rows - 1, p->d.rows - 2, d_bottom, p->bucket_shift, s));
-  const int check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
-  WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));  // returns at once if nothing woke up
+  WS_CUDA(ctx, launch_flood(p->fb, p->d, p->check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));  // returns at once if nothing woke up
   p->stats[4] += 3;
   WS_TRY(check_flood_errors(p));
   *changed = p->h_ctrl[FC_STRIP_CHANGED] ? 1 : 0;
@@ -685,7 +701,7 @@ extern "C" ws_status ws_plan_strip_labels(ws_plan* p) {
   if (!p) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
-  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, ctx->stream));
+  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, p->cfg.tie_break == WS_TIE_RANDOM, ctx->tie_seed, ctx->stream));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, ctx->stream));
   p->stats[4] += 2;
   WS_TRY(check_flood_errors(p));
@@ -1202,30 +1218,25 @@ extern "C" ws_status ws_transform_lake_counts(ws_ctx* ctx, const ws_config* cfg,
   return WS_OK;
 }
 
-extern "C" ws_status ws_transform_to_list(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
-                                          const uint64_t* seeds_rc, size_t nseeds, uint8_t* out_levels,
-                                          uint64_t* out_sizes) {
-  if (!ctx || !out_sizes) return WS_ERR_INVALID_ARG;
-  HostRun hr;
-  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
-  ws_plan* p = hr.plan;
+// find_lake_sizes (lib.rs:629-635) for every level, on the device: d_sizes[l][c], c = 0..nseeds (row length
+// ncol = nseeds + 1; column 0 = uncoloured pixels).  Labels never exceed nseeds, so the rest of the reference's
+// (rows*cols + 1)-long rows is zero.  The caller frees *d_sizes_out with cudaFree.
+static ws_status lake_sizes_device(ws_ctx* ctx, ws_plan* p, const ws_config* cfg, size_t npx, size_t ncol,
+                                   uint64_t** d_sizes_out) {
   cudaStream_t s = ctx->stream;
   const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
-  const size_t ncol = nseeds + 1;  // labels never exceed nseeds: the rest of each row is zero
-  if ((double)ncol * nlev * 12.0 > 64e9) return fail(ctx, WS_ERR_TOO_LARGE, "transform_to_list: nseeds x levels too large");
   uint32_t* d_cnt = nullptr;
   uint64_t* d_sizes = nullptr;
   uint64_t* d_scratch = nullptr;
   cudaError_t e = cudaMalloc((void**)&d_cnt, ncol * nlev * 4);
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_sizes, ncol * nlev * 8);
   if (e == cudaSuccess) e = cudaMalloc((void**)&d_scratch, ncol * 8);
-  ws_status st = WS_OK;
   auto body = [&]() -> ws_status {
     WS_CUDA(ctx, e);
     WS_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, ncol * nlev * 4, s));
     WS_CUDA(ctx, cudaMemsetAsync(d_sizes, 0, ncol * nlev * 8, s));
-    WS_CUDA(ctx, launch_colour_level_count(p->fb.lab, p->fb.lvl, hr.npx, (uint32_t)ncol, d_cnt, s));
-    WS_CUDA(ctx, launch_sizes_cumulate(d_cnt, (uint32_t)ncol, nlev, hr.npx, d_sizes, s));
+    WS_CUDA(ctx, launch_colour_level_count(p->fb.lab, p->fb.lvl, npx, (uint32_t)ncol, d_cnt, s));
+    WS_CUDA(ctx, launch_sizes_cumulate(d_cnt, (uint32_t)ncol, nlev, npx, d_sizes, s));
     p->stats[4] += 3;
     if (cfg->kind == WS_MERGING) {
       for (uint32_t l = 0; l < nlev; ++l) {
@@ -1234,20 +1245,80 @@ extern "C" ws_status ws_transform_to_list(ws_ctx* ctx, const ws_config* cfg, con
         p->stats[4] += 1;
       }
     }
-    // rows of length npx+1 on the host (find_lake_sizes, lib.rs:630): zero, then the first ncol entries
-    const size_t row = hr.npx + 1;
-    memset(out_sizes, 0, (size_t)nlev * row * sizeof(uint64_t));
-    WS_CUDA(ctx, cudaMemcpy2DAsync(out_sizes, row * 8, d_sizes, ncol * 8, ncol * 8, nlev, cudaMemcpyDeviceToHost, s));
-    WS_CUDA(ctx, cudaStreamSynchronize(s));
     return WS_OK;
   };
-  st = body();
+  const ws_status st = body();
+  cudaStreamSynchronize(s);
   cudaFree(d_cnt);
-  cudaFree(d_sizes);
   cudaFree(d_scratch);
-  if (st == WS_OK && out_levels)
-    for (uint32_t l = 0; l < nlev; ++l) out_levels[l] = (uint8_t)l;
+  if (st != WS_OK) {
+    cudaFree(d_sizes);
+    d_sizes = nullptr;
+  }
+  *d_sizes_out = d_sizes;
   return st;
+}
+
+static ws_status lake_sizes_guard(ws_ctx* ctx, const ws_config* cfg, size_t nseeds) {
+  const double cells = (double)(nseeds + 1) * ((double)cfg->max_water_level + 1.0);
+  if (cells * 12.0 > 64e9) return fail(ctx, WS_ERR_TOO_LARGE, "lake sizes: (nseeds + 1) x levels too large");
+  return WS_OK;
+}
+
+extern "C" ws_status ws_transform_to_list(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
+                                          const uint64_t* seeds_rc, size_t nseeds, uint8_t* out_levels,
+                                          uint64_t* out_sizes) {
+  if (!ctx || !out_sizes) return WS_ERR_INVALID_ARG;
+  WS_TRY(check_cfg(ctx, cfg));
+  WS_TRY(lake_sizes_guard(ctx, cfg, nseeds));  // before any work is done
+  HostRun hr;
+  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
+  ws_plan* p = hr.plan;
+  cudaStream_t s = ctx->stream;
+  const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
+  const size_t ncol = nseeds + 1;
+  uint64_t* d_sizes = nullptr;
+  WS_TRY(lake_sizes_device(ctx, p, cfg, hr.npx, ncol, &d_sizes));
+  // rows of length npx+1 on the host (find_lake_sizes, lib.rs:630): zero, then the first entries.  With more
+  // seeds than pixels (duplicate positions are legal) the colours that survive still fit the row: a colour
+  // > npx on the canvas would make the reference index out of bounds (lib.rs:633) -- clamp the copied width.
+  const size_t row = hr.npx + 1;
+  const size_t width = std::min(ncol, row);
+  memset(out_sizes, 0, (size_t)nlev * row * sizeof(uint64_t));
+  cudaError_t e = cudaMemcpy2DAsync(out_sizes, row * 8, d_sizes, ncol * 8, width * 8, nlev, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_sizes);
+  WS_CUDA(ctx, e);
+  if (out_levels)
+    for (uint32_t l = 0; l < nlev; ++l) out_levels[l] = (uint8_t)l;
+  return WS_OK;
+}
+
+extern "C" ws_status ws_transform_lake_sizes_compact(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
+                                                     const uint64_t* seeds_rc, size_t nseeds,
+                                                     uint64_t* out_lake_counts, uint64_t* out_sizes) {
+  if (!ctx || !out_sizes) return WS_ERR_INVALID_ARG;
+  WS_TRY(check_cfg(ctx, cfg));
+  WS_TRY(lake_sizes_guard(ctx, cfg, nseeds));
+  HostRun hr;
+  WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
+  cudaStream_t s = ctx->stream;
+  const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
+  const size_t ncol = nseeds + 1;
+  uint64_t* d_sizes = nullptr;
+  WS_TRY(lake_sizes_device(ctx, hr.plan, cfg, hr.npx, ncol, &d_sizes));
+  cudaError_t e = cudaMemcpyAsync(out_sizes, d_sizes, (size_t)nlev * ncol * 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_sizes);
+  WS_CUDA(ctx, e);
+  if (out_lake_counts)  // lakes = colours with at least one pixel
+    for (uint32_t l = 0; l < nlev; ++l) {
+      uint64_t n = 0;
+      const uint64_t* r = out_sizes + (size_t)l * ncol;
+      for (size_t c = 1; c < ncol; ++c) n += (r[c] != 0);
+      out_lake_counts[l] = n;
+    }
+  return WS_OK;
 }
 
 extern "C" ws_status ws_transform_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs, size_t n_img,
@@ -1256,8 +1327,14 @@ extern "C" ws_status ws_transform_batch(ws_ctx* ctx, const ws_config* cfg, const
                                         uint64_t* out_lake_counts) {
   if (!ctx || !imgs || !seed_offsets) return WS_ERR_INVALID_ARG;
   if (n_img == 0 || rows == 0 || cols == 0) return fail(ctx, WS_ERR_INVALID_ARG, "empty image");
+  WS_TRY(check_cfg(ctx, cfg));
+  if (out_lake_counts && cfg->kind != WS_MERGING)
+    return fail(ctx, WS_ERR_INVALID_ARG, "lake counts need kind = WS_MERGING");
+  // seed_offsets[0..n_img]: starts at 0, ascending, total below 2^31 (colours are 31-bit on the device)
+  if (seed_offsets[0] != 0) return fail(ctx, WS_ERR_INVALID_ARG, "seed_offsets[0] must be 0");
   for (size_t b = 0; b < n_img; ++b)
     if (seed_offsets[b] > seed_offsets[b + 1]) return fail(ctx, WS_ERR_INVALID_ARG, "seed_offsets must be ascending");
+  if (seed_offsets[n_img] >= 0x7fffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "more than 2^31 - 2 seeds");
   const size_t nseeds = (size_t)seed_offsets[n_img];
   HostRun hr;
   WS_TRY(host_run_batch(ctx, cfg, imgs, nullptr, n_img, rows, cols, seeds_rc, seed_offsets, nseeds, &hr));
@@ -1280,7 +1357,6 @@ extern "C" ws_status ws_transform_batch(ws_ctx* ctx, const ws_config* cfg, const
     WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   }
   if (out_lake_counts) {
-    if (cfg->kind != WS_MERGING) return fail(ctx, WS_ERR_INVALID_ARG, "lake counts need kind = WS_MERGING");
     std::vector<uint32_t> h(n_img * 256);
     WS_CUDA(ctx, cudaMemcpyAsync(h.data(), p->mb.counts, n_img * 256 * 4, cudaMemcpyDeviceToHost, s));
     WS_CUDA(ctx, cudaStreamSynchronize(s));

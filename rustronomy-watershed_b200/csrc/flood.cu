@@ -144,10 +144,15 @@ __device__ __forceinline__ bool push_mark(const FloodBuffers& b, uint32_t tile, 
 }
 // part 2: reserve a slot, write it, raise the semaphore.  No fence between the two: a taker that wins a
 // slot before its tile id has landed simply waits for it (the slot holds Q_EMPTY until then).
+// The slot must be free: the ring holds tiles + FLOOD_QSLACK entries, at most one live entry per tile and
+// bucket plus the claims in flight -- but a claimer stalled between taking its head index and reading the
+// slot for a whole lap of the ring would be overwritten silently.  The exchange makes that loud (error bit 5)
+// instead of losing a tile; its result is not waited for before the semaphore is raised.
 __device__ __forceinline__ void push_append(const FloodBuffers& b, uint32_t tile, uint32_t bucket) {
   const uint32_t t = atomicAdd(&b.ctrl[FC_QTAIL0 + bucket], 1u);
-  st_cg(&b.qslots[(size_t)bucket * b.qcap + t % b.qcap], tile);
+  const uint32_t old = atomicExch(&b.qslots[(size_t)bucket * b.qcap + t % b.qcap], tile);
   atomicAdd(&b.ctrl[FC_QAVAIL0 + bucket], 1u);
+  if (old != Q_EMPTY) atomicOr(&b.ctrl[FC_ERROR], 32u);
 }
 template <bool kQuiescent>
 __device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t tile, uint32_t bucket) {
@@ -596,7 +601,7 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
         if (retired) continue;
         if (busy) {
           // our own consumers are still iterating
-        } else if (ld_poll(&a.b.ctrl[FC_OUTSTANDING]) == 0u || (ld_poll(&a.b.ctrl[FC_ERROR]) & 24u)) {
+        } else if (ld_poll(&a.b.ctrl[FC_OUTSTANDING]) == 0u || (ld_poll(&a.b.ctrl[FC_ERROR]) & 56u)) {
           break;  // nothing queued, nothing in flight anywhere: the fixed point is reached
         }
         __nanosleep(100);

@@ -14,7 +14,8 @@ enum FloodCtrl {
   FC_IDLE = 3,         // idle polls of the producer warps
   FC_WAIT_KCYC = 4,    // consumers: kilo-cycles waiting for a staged tile (tail at the end of the flood excluded)
   FC_BUSY_KCYC = 5,    // consumers: kilo-cycles iterating
-  FC_ERROR = 8,        // bit 0: seed out of bounds, bit 1: hop overflow, bit 2: orphan pixel, bit 3: flood watchdog
+  FC_ERROR = 8,        // bit 0: seed out of bounds, bit 1: hop overflow, bit 2: orphan pixel, bit 3: slot never written,
+                       // bit 4: flood watchdog, bit 5: a ring slot was overwritten while still in use
   FC_JUMP_FLAG0 = 9,   // [9..11] rotating "still unresolved" flags of the pointer jumping
   FC_JUMP_ROUNDS = 12,
   FC_STRIP_CHANGED = 13,  // a halo row of arrival times got lower on import
@@ -91,7 +92,9 @@ cudaError_t launch_unpad_T(const uint32_t* Tp, ImageDims d, uint32_t* out, cudaS
 // --- labels (colour decision of lib.rs:235-255 with the `col0` tie-break) ---
 size_t rim_words(const ImageDims& d);
 // also counts, per slice, the owned pixels that hold a seed = colours present on the canvas (ndistinct[n_img])
-cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, cudaStream_t s);
+// tie_random: draw the parent uniformly among the earlier neighbours (lib.rs:250-253) instead of taking the first
+cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, bool tie_random, uint64_t tie_seed,
+                          cudaStream_t s);
 cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s);
 
 // --- merging (find_merge + make_colour_map + recolour, lib.rs:393-542, 590-592) ---

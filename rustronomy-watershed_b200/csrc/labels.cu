@@ -53,8 +53,17 @@ struct __align__(128) LabelSmem {
   uint32_t nseed_px;
 };
 
+// counter-based generator of the random tie-break: splitmix64 of (key, position of the pixel in the field)
+__device__ __forceinline__ uint32_t tie_hash(uint64_t key, uint64_t idx) {
+  uint64_t z = key + (idx + 1ull) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+
+template <bool kTieRandom>
 __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, ImageDims d,
-                                                                uint32_t* __restrict__ ndistinct) {
+                                                                uint32_t* __restrict__ ndistinct, uint64_t tie_seed) {
   __shared__ LabelSmem sm;
   const int tid = threadIdx.x;
   const int tpi = d.tiles_per_img();
@@ -104,7 +113,24 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
       } else {
         // A coloured non-seed pixel is interior, so all four neighbours exist.
         int dr = 0, dc = 0;
-        if (t[LT_W] < tv) dr = 1;
+        if (kTieRandom) {
+          // the reference draws uniformly among the coloured neighbours, in the order down, right, left, up
+          const uint32_t em = (t[LT_W] < tv ? 1u : 0u) | (t[1] < tv ? 2u : 0u) | (t[-1] < tv ? 4u : 0u) |
+                              (t[-LT_W] < tv ? 8u : 0u);
+          const int k = __popc(em);
+          if (k == 0) {
+            atomicOr(&b.ctrl[FC_ERROR], 4u);
+          } else {
+            int pick = 0;
+            if (k > 1) {
+              const uint64_t pos = ((uint64_t)img * (uint64_t)d.global_rows + (uint64_t)(r + d.row_offset)) * (uint64_t)d.cols + (uint64_t)c;
+              pick = (int)(((uint64_t)tie_hash(tie_seed, pos) * (uint64_t)k) >> 32);
+            }
+            const int bit = __fns(em, 0, pick + 1);  // position of the pick-th set bit
+            dr = bit == 0 ? 1 : (bit == 3 ? -1 : 0);
+            dc = bit == 1 ? 1 : (bit == 2 ? -1 : 0);
+          }
+        } else if (t[LT_W] < tv) dr = 1;
         else if (t[1] < tv) dc = 1;
         else if (t[-1] < tv) dc = -1;
         else if (t[-LT_W] < tv) dr = -1;
@@ -171,10 +197,12 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   }
 }
 
-cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, cudaStream_t s) {
+cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, bool tie_random, uint64_t tie_seed,
+                          cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(ndistinct, 0, sizeof(uint32_t) * (size_t)d.n_img, s);
   if (e != cudaSuccess) return e;
-  label_tile_kernel<<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d, ndistinct);
+  if (tie_random) label_tile_kernel<true><<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d, ndistinct, tie_seed);
+  else label_tile_kernel<false><<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d, ndistinct, 0ull);
   return cudaGetLastError();
 }
 

@@ -42,3 +42,16 @@ def oracle():
 def fields():
     import fieldgen
     return fieldgen
+
+
+_BIG = {}
+
+
+def big_field(kind: str, size: int):
+    """The 16384^2 / 8192^2 fields of the full-size tests, generated once per session (the smoothed one costs an
+    FFT of 268 M points)."""
+    import fieldgen
+    key = (kind, size)
+    if key not in _BIG:
+        _BIG[key] = fieldgen.uniform(size, size, 0) if kind == "uniform" else fieldgen.smooth(size, size, 16.0, 0)
+    return _BIG[key]

@@ -15,6 +15,7 @@ import pytest
 import torch
 
 import fieldgen
+from conftest import big_field
 from wsb200_loader import load
 
 pytestmark = pytest.mark.gpu
@@ -47,7 +48,7 @@ def _shift(x, dr, dc, fill):
 
 def _run(kind, S, field):
     ws = load()
-    img = {"uniform": lambda: fieldgen.uniform(S, S, 0), "smooth": lambda: fieldgen.smooth(S, S, 16.0, 0)}[field]()
+    img = big_field(field, S)
     ctx = ws.default_context()
     plan = ws.Plan(ctx, 1, S, S)
     d_img = torch.from_numpy(img).cuda()
