@@ -9,6 +9,7 @@
 //   edge_scan -> red_scatter -> uf_init -> union_levels (persistent, cooperative) -> lake_counts;
 //   the merge tree for per-level representatives is built on demand (plan_build_tree)
 #include "../../include/ws_b200.h"
+#include "hostpipe.h"
 #include "kernels.cuh"
 
 #include <algorithm>
@@ -45,6 +46,13 @@ struct ws_ctx {
   uint64_t* d_out[2] = {nullptr, nullptr}; size_t d_out_cap[2] = {0, 0};
   uint64_t* h_pin[2] = {nullptr, nullptr}; size_t h_pin_cap[2] = {0, 0};
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  // pageable caller memory: worker threads + a ring of page-locked slots (hostpipe.h), made on first use
+  HostPool pool;
+  int host_threads = 0;            // 0: not started yet
+  int host_threads_wanted = 0;     // 0: default (min(16, CPUs this process may use), WS_HOST_THREADS)
+  bool pinned_host_widen = false;  // page-locked label outputs: u32 over the link + widening by the workers
+  uint8_t* ring = nullptr;
+  cudaEvent_t ring_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct ws_plan {
@@ -214,6 +222,7 @@ extern "C" ws_status ws_ctx_create(int device, ws_ctx** out) {
     cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
   }
+  if (const char* e = getenv("WS_PINNED_HOST_WIDEN")) c->pinned_host_widen = atoi(e) != 0;
   c->flood_grid = flood_max_grid(device);
   c->jump_grid = jump_max_grid(device);
   c->union_grid = union_max_grid(device);
@@ -238,6 +247,10 @@ extern "C" void ws_ctx_destroy(ws_ctx* c) {
   cudaFree(c->d_seeds64);
   cudaFree(c->d_pp_scratch);
   cudaFree(c->d_seed_off);
+  c->pool.stop();
+  if (c->ring) cudaFreeHost(c->ring);
+  for (auto& ev : c->ring_ev)
+    if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) {
     cudaFree(c->d_out[i]);
     if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
@@ -253,6 +266,24 @@ extern "C" ws_status ws_ctx_set_tie_seed(ws_ctx* ctx, uint64_t seed) {
   if (!ctx) return WS_ERR_INVALID_ARG;
   ctx->tie_seed = seed;
   return WS_OK;
+}
+
+extern "C" ws_status ws_ctx_set_host_threads(ws_ctx* ctx, int nthreads) {
+  if (!ctx || nthreads < 0 || nthreads > 64) return WS_ERR_INVALID_ARG;
+  ctx->host_threads_wanted = nthreads;
+  if (ctx->host_threads) {  // restart with the new size on the next staged copy
+    ctx->pool.stop();
+    ctx->host_threads = 0;
+  }
+  return WS_OK;
+}
+
+extern "C" ws_status ws_ctx_set_option(ws_ctx* ctx, ws_option opt, int value) {
+  if (!ctx) return WS_ERR_INVALID_ARG;
+  switch (opt) {
+    case WS_OPT_PINNED_HOST_WIDEN: ctx->pinned_host_widen = value != 0; return WS_OK;
+  }
+  return fail(ctx, WS_ERR_INVALID_ARG, "unknown option");
 }
 
 extern "C" void* ws_ctx_stream(ws_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -413,9 +444,9 @@ static ws_status plan_merge(ws_plan* p) {
     uint32_t st[16];
     cudaStreamSynchronize(s);
     cudaMemcpy(st, p->mb.red_count, 64, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "merge stats: edges %u | tiles with edges %u, rounds stage0 %.2f stage1 %.2f per tile, live-edge looks "
-            "stage0 %.1f stage1 %.1f per tile, ids %.1f, out %.1f per tile\n", st[0], st[8], st[4] / (double)st[8],
-            st[5] / (double)st[8], st[6] / (double)st[8], st[7] / (double)st[8], st[9] / (double)st[8], st[10] / (double)st[8]);
+    fprintf(stderr, "merge stats: edges %u | tiles with edges %u, rounds %.2f per tile, live-edge looks %.1f per tile, "
+            "ids %.1f, out %.1f per tile\n", st[0], st[8], st[4] / (double)st[8], st[6] / (double)st[8],
+            st[9] / (double)st[8], st[10] / (double)st[8]);
   }
 #endif
   WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, 0, p->seed_off, p->d.n_img,
@@ -833,23 +864,157 @@ ws_status check_image(ws_ctx* ctx, const ws_image* img) {
   return WS_OK;
 }
 
+// ---- staged copies between pageable caller memory and the device (hostpipe.h) --------------------------
+constexpr size_t RING_SLOT_BYTES = (size_t)32 << 20;
+constexpr int RING_SLOTS = 4;
+
+ws_status ensure_ring(ws_ctx* ctx) {
+  if (!ctx->host_threads) {
+    const int n = ctx->host_threads_wanted > 0 ? ctx->host_threads_wanted : host_threads_default();
+    ctx->pool.start(n);
+    ctx->host_threads = n;
+  }
+  if (!ctx->ring) {
+    WS_CUDA(ctx, cudaHostAlloc((void**)&ctx->ring, RING_SLOT_BYTES * RING_SLOTS, cudaHostAllocDefault));
+    for (int i = 0; i < RING_SLOTS; ++i) WS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+  }
+  return WS_OK;
+}
+
+// a chunk of `n` bytes split over the pool in pieces that are multiples of 64 bytes
+template <typename F>
+void pool_split(ws_ctx* ctx, size_t n, F&& piece) {
+  const size_t want = std::max<size_t>(1, std::min<size_t>((size_t)ctx->pool.size(), n >> 18));
+  const size_t per = ((n + want - 1) / want + 63) & ~(size_t)63;
+  const size_t parts = (n + per - 1) / per;
+  ctx->pool.run(parts, [&](size_t t) {
+    const size_t lo = t * per, hi = std::min(n, lo + per);
+    if (lo < hi) piece(lo, hi - lo);
+  });
+}
+
+// Host -> device through the ring: fill(slot pointer, byte offset in the destination, bytes) is run by the
+// workers for every piece while the copy engine moves the previous slot.
+template <typename Fill>
+ws_status staged_h2d(ws_ctx* ctx, void* d_dst, size_t total, Fill fill) {
+  if (total == 0) return WS_OK;
+  WS_TRY(ensure_ring(ctx));
+  cudaStream_t s = ctx->stream;
+  const size_t nchunks = (total + RING_SLOT_BYTES - 1) / RING_SLOT_BYTES;
+  for (size_t k = 0; k < nchunks; ++k) {
+    const int slot = (int)(k % RING_SLOTS);
+    if (k >= (size_t)RING_SLOTS) WS_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
+    const size_t off = k * RING_SLOT_BYTES, n = std::min(RING_SLOT_BYTES, total - off);
+    uint8_t* sp = ctx->ring + (size_t)slot * RING_SLOT_BYTES;
+    pool_split(ctx, n, [&](size_t lo, size_t len) { fill(sp + lo, off + lo, len); });
+    WS_CUDA(ctx, cudaMemcpyAsync((char*)d_dst + off, sp, n, cudaMemcpyHostToDevice, s));
+    WS_CUDA(ctx, cudaEventRecord(ctx->ring_ev[slot], s));
+  }
+  // the ring may be reused by the next staged copy: its slots are guarded by the same events
+  return WS_OK;
+}
+
+// Device -> host through the ring, RING_SLOTS - 1 copies in flight ahead of the workers:
+// drain(slot pointer, byte offset in the source, bytes).
+template <typename Drain>
+ws_status staged_d2h(ws_ctx* ctx, const void* d_src, size_t total, Drain drain) {
+  if (total == 0) return WS_OK;
+  WS_TRY(ensure_ring(ctx));
+  cudaStream_t s = ctx->stream;
+  // (slots still in flight from an earlier staged_h2d on this stream are ordered before these copies)
+  const size_t nchunks = (total + RING_SLOT_BYTES - 1) / RING_SLOT_BYTES;
+  for (size_t k = 0; k < nchunks + RING_SLOTS - 1; ++k) {
+    if (k < nchunks) {
+      const int slot = (int)(k % RING_SLOTS);
+      const size_t off = k * RING_SLOT_BYTES, n = std::min(RING_SLOT_BYTES, total - off);
+      WS_CUDA(ctx, cudaMemcpyAsync(ctx->ring + (size_t)slot * RING_SLOT_BYTES, (const char*)d_src + off, n,
+                                   cudaMemcpyDeviceToHost, s));
+      WS_CUDA(ctx, cudaEventRecord(ctx->ring_ev[slot], s));
+    }
+    if (k + 1 >= (size_t)RING_SLOTS) {
+      const size_t j = k + 1 - RING_SLOTS;
+      if (j < nchunks) {
+        const int slot = (int)(j % RING_SLOTS);
+        const size_t off = j * RING_SLOT_BYTES, n = std::min(RING_SLOT_BYTES, total - off);
+        WS_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
+        const uint8_t* sp = ctx->ring + (size_t)slot * RING_SLOT_BYTES;
+        pool_split(ctx, n, [&](size_t lo, size_t len) { drain(sp + lo, off + lo, len); });
+      }
+    }
+  }
+  return WS_OK;
+}
+
+// plain bytes: page-locked memory goes straight over the link, pageable memory through the ring
+ws_status copy_h2d(ws_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return WS_OK;
+  if (bytes < ((size_t)1 << 20) || host_ptr_is_pinned(h_src)) {
+    WS_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return WS_OK;
+  }
+  return staged_h2d(ctx, d_dst, bytes, [&](uint8_t* sp, size_t off, size_t n) { memcpy(sp, (const char*)h_src + off, n); });
+}
+ws_status copy_d2h(ws_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return WS_OK;
+  if (bytes < ((size_t)1 << 20) || host_ptr_is_pinned(h_dst)) {
+    WS_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return WS_OK;
+  }
+  return staged_d2h(ctx, d_src, bytes, [&](const uint8_t* sp, size_t off, size_t n) { memcpy((char*)h_dst + off, sp, n); });
+}
+
 // Upload an ArrayView2<u8> (arbitrary strides) as a dense C-order device image.
 ws_status upload_image(ws_ctx* ctx, const ws_image* img, uint8_t* dst) {
   cudaStream_t s = ctx->stream;
   const size_t rows = img->rows, cols = img->cols;
-  if (img->col_stride == 1 && img->row_stride == (ptrdiff_t)cols) {
-    WS_CUDA(ctx, cudaMemcpyAsync(dst, img->data, rows * cols, cudaMemcpyHostToDevice, s));
-  } else if (img->col_stride == 1 && img->row_stride > (ptrdiff_t)cols) {
+  if (img->col_stride == 1 && img->row_stride == (ptrdiff_t)cols) return copy_h2d(ctx, dst, img->data, rows * cols);
+  if (img->col_stride == 1 && img->row_stride > (ptrdiff_t)cols && host_ptr_is_pinned(img->data)) {
     WS_CUDA(ctx, cudaMemcpy2DAsync(dst, cols, img->data, (size_t)img->row_stride, cols, rows,
                                    cudaMemcpyHostToDevice, s));
-  } else {  // general strides (transposed / reversed views): repack on the host
-    std::vector<uint8_t> tmp(rows * cols);
-    for (size_t r = 0; r < rows; ++r)
-      for (size_t c = 0; c < cols; ++c)
-        tmp[r * cols + c] = img->data[(ptrdiff_t)r * img->row_stride + (ptrdiff_t)c * img->col_stride];
-    WS_CUDA(ctx, cudaMemcpyAsync(dst, tmp.data(), rows * cols, cudaMemcpyHostToDevice, s));
-    WS_CUDA(ctx, cudaStreamSynchronize(s));  // tmp dies here
+    return WS_OK;
   }
+  // general strides (sub-views, transposed / reversed views): the workers gather into the ring
+  const uint8_t* base = img->data;
+  const ptrdiff_t rs = img->row_stride, cs = img->col_stride;
+  return staged_h2d(ctx, dst, rows * cols, [=](uint8_t* sp, size_t off, size_t n) {
+    size_t r = off / cols, c = off - r * cols;
+    for (size_t i = 0; i < n; ++i) {
+      sp[i] = base[(ptrdiff_t)r * rs + (ptrdiff_t)c * cs];
+      if (++c == cols) { c = 0; ++r; }
+    }
+  });
+}
+
+// Final segmenting labels of `n` pixels as usize into caller memory.  Pageable destination (an ordinary
+// Array2<usize>): the u32 label words cross the link as they are and the workers widen them out of the ring
+// -- half the bytes on the link and no extra pass over the destination.  Page-locked destination: widened
+// on the device chunk by chunk, copied by the second copy engine while the next chunk is widened (or the
+// pageable way if the caller asked for it: WS_OPT_PINNED_HOST_WIDEN).
+ws_status download_labels_u64(ws_ctx* ctx, ws_plan* p, const uint32_t* d_lab, size_t n, uint64_t* out) {
+  cudaStream_t s = ctx->stream;
+  if (!host_ptr_is_pinned(out) || ctx->pinned_host_widen) {
+    WS_TRY(staged_d2h(ctx, d_lab, n * 4, [=](const uint8_t* sp, size_t off, size_t len) {
+      widen_labels_host(out + off / 4, reinterpret_cast<const uint32_t*>(sp), len / 4);
+    }));
+    WS_CUDA(ctx, cudaStreamSynchronize(s));
+    return WS_OK;
+  }
+  const size_t chunk = (size_t)8 << 20;  // pixels per chunk: 64 MB of usize
+  for (int i = 0; i < 2; ++i) WS_TRY(grow(ctx, ctx->d_out[i], ctx->d_out_cap[i], std::min(chunk, n)));
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, ++k) {
+    const int buf = (int)(k & 1);
+    const size_t m = std::min(chunk, n - off);
+    if (k >= 2) WS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_copied[buf], 0));
+    WS_CUDA(ctx, launch_widen_labels(d_lab + off, m, ctx->d_out[buf], s));
+    WS_CUDA(ctx, cudaEventRecord(ctx->ev_ready[buf], s));
+    WS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[buf], 0));
+    WS_CUDA(ctx, cudaMemcpyAsync(out + off, ctx->d_out[buf], m * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    WS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+    p->stats[4] += 1;
+  }
+  WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  WS_CUDA(ctx, cudaStreamSynchronize(s));
   return WS_OK;
 }
 
@@ -871,13 +1036,20 @@ ws_status get_plan(ws_ctx* ctx, size_t n_img, size_t rows, size_t cols, ws_plan*
 struct HostRun {
   ws_plan* plan = nullptr;
   size_t orows = 0, ocols = 0, npx = 0;
+  size_t nseeds = 0;  // as given, or as found on the device (WS_SEEDS_AUTO)
 };
 
 ws_status host_run_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs, const ws_image* view, size_t n_img,
                          size_t rows, size_t cols, const uint64_t* seeds_rc, const uint64_t* seed_offsets,
                          size_t nseeds, HostRun* hr) {
   WS_TRY(check_cfg(ctx, cfg));
-  if (nseeds && !seeds_rc) return fail(ctx, WS_ERR_INVALID_ARG, "seeds is NULL");
+  const bool auto_seeds = nseeds == WS_SEEDS_AUTO;
+  if (!auto_seeds && nseeds && !seeds_rc) return fail(ctx, WS_ERR_INVALID_ARG, "seeds is NULL");
+  if (!auto_seeds && nseeds >= 0x7fffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "more than 2^31 - 2 seeds");
+  // the reference's caller finds the seeds on the UNPADDED image and hands them over unshifted
+  // (lib.rs:1365-1367): that needs the caller's own list
+  if (auto_seeds && cfg->edge_correction)
+    return fail(ctx, WS_ERR_INVALID_ARG, "WS_SEEDS_AUTO is not available with edge correction");
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   size_t orows, ocols;
   ws_output_shape(cfg, rows, cols, &orows, &ocols);
@@ -889,34 +1061,53 @@ ws_status host_run_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs,
   if (cfg->edge_correction) {
     WS_TRY(grow(ctx, ctx->d_raw, ctx->d_raw_cap, n_img * npx_in));
     if (view) WS_TRY(upload_image(ctx, view, ctx->d_raw));
-    else WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_raw, imgs, n_img * npx_in, cudaMemcpyHostToDevice, s));
+    else WS_TRY(copy_h2d(ctx, ctx->d_raw, imgs, n_img * npx_in));
     for (size_t b = 0; b < n_img; ++b)
       WS_CUDA(ctx, launch_pad_image(ctx->d_raw + b * npx_in, (int)rows, (int)cols, ctx->d_img + b * npx_out, s));
   } else {
     if (view) WS_TRY(upload_image(ctx, view, ctx->d_img));
-    else WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_img, imgs, n_img * npx_in, cudaMemcpyHostToDevice, s));
+    else WS_TRY(copy_h2d(ctx, ctx->d_img, imgs, n_img * npx_in));
   }
-  // seeds: the (usize, usize) pairs go up as they are; a kernel narrows them to u32 pairs and marks
-  // the ones outside the (padded) output shape -- the reference indexes output[seed] and panics there
-  p->h_seed_off.assign(n_img + 1, 0);
-  if (seed_offsets) {
-    for (size_t b = 0; b <= n_img; ++b) p->h_seed_off[b] = (uint32_t)seed_offsets[b];
-  } else {
-    p->h_seed_off[n_img] = (uint32_t)nseeds;
-  }
-  WS_TRY(grow(ctx, ctx->d_seeds, ctx->d_seeds_cap, 2 * nseeds));
   WS_TRY(grow(ctx, ctx->d_seed_off, ctx->d_seed_off_cap, n_img + 1));
-  if (nseeds) {
-    WS_TRY(grow(ctx, ctx->d_seeds64, ctx->d_seeds64_cap, 2 * nseeds));
-    WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds64, seeds_rc, 2 * nseeds * 8, cudaMemcpyHostToDevice, s));
-    WS_CUDA(ctx, launch_seeds_convert(ctx->d_seeds64, ctx->d_seeds, nseeds, orows, ocols, s));
+  if (auto_seeds) {
+    // WatershedUtils::find_local_minima on the device: nothing but the image crosses the link
+    size_t total = 0;
+    WS_TRY(ws_plan_find_local_minima(p, ctx->d_img, nullptr, 0, ctx->d_seed_off, &total));
+    if (total >= 0x7fffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "more than 2^31 - 2 seeds");
+    WS_TRY(grow(ctx, ctx->d_seeds, ctx->d_seeds_cap, 2 * total));
+    if (total) WS_CUDA(ctx, launch_minima_write(ctx->d_img, p->d, p->chunk_counts, ctx->d_seeds, (uint32_t)total, s));
+    nseeds = total;
+  } else {
+    // seeds: the (usize, usize) pairs become u32 pairs, those outside the (padded) output shape are marked
+    // -- the reference indexes output[seed] and panics there.  Page-locked lists go up as they are and a
+    // kernel narrows them; pageable lists are narrowed by the workers on their way into the ring.
+    p->h_seed_off.assign(n_img + 1, 0);
+    if (seed_offsets) {
+      for (size_t b = 0; b <= n_img; ++b) p->h_seed_off[b] = (uint32_t)seed_offsets[b];
+    } else {
+      p->h_seed_off[n_img] = (uint32_t)nseeds;
+    }
+    WS_TRY(grow(ctx, ctx->d_seeds, ctx->d_seeds_cap, 2 * nseeds));
+    if (nseeds) {
+      if (nseeds * 16 < ((size_t)1 << 20) || host_ptr_is_pinned(seeds_rc)) {
+        WS_TRY(grow(ctx, ctx->d_seeds64, ctx->d_seeds64_cap, 2 * nseeds));
+        WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seeds64, seeds_rc, 2 * nseeds * 8, cudaMemcpyHostToDevice, s));
+        WS_CUDA(ctx, launch_seeds_convert(ctx->d_seeds64, ctx->d_seeds, nseeds, orows, ocols, s));
+      } else {
+        const uint64_t lr = orows, lc = ocols;
+        WS_TRY(staged_h2d(ctx, ctx->d_seeds, 2 * nseeds * 4, [=](uint8_t* sp, size_t off, size_t n) {
+          narrow_seeds_host(reinterpret_cast<uint32_t*>(sp), seeds_rc + off / 4, n / 4, off / 4, lr, lc);
+        }));
+      }
+    }
+    WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seed_off, p->h_seed_off.data(), (n_img + 1) * 4, cudaMemcpyHostToDevice, s));
   }
-  WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seed_off, p->h_seed_off.data(), (n_img + 1) * 4, cudaMemcpyHostToDevice, s));
   WS_TRY(ws_plan_run(p, cfg, ctx->d_img, ctx->d_seeds, ctx->d_seed_off, nseeds));
   hr->plan = p;
   hr->orows = orows;
   hr->ocols = ocols;
   hr->npx = npx_out;
+  hr->nseeds = nseeds;
   return WS_OK;
 }
 
@@ -1118,12 +1309,7 @@ extern "C" ws_status ws_transform(ws_ctx* ctx, const ws_config* cfg, const ws_im
   }
   HostRun hr;
   WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
-  WS_TRY(grow(ctx, ctx->d_out[0], ctx->d_out_cap[0], hr.npx));
-  WS_CUDA(ctx, launch_widen_labels(hr.plan->fb.lab, hr.npx, ctx->d_out[0], ctx->stream));
-  WS_CUDA(ctx, cudaMemcpyAsync(out_labels, ctx->d_out[0], hr.npx * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  hr.plan->stats[4] += 1;
-  return WS_OK;
+  return download_labels_u64(ctx, hr.plan, hr.plan->fb.lab, hr.npx, out_labels);
 }
 
 extern "C" ws_status ws_transform_compact(ws_ctx* ctx, const ws_config* cfg, const ws_image* img,
@@ -1133,13 +1319,21 @@ extern "C" ws_status ws_transform_compact(ws_ctx* ctx, const ws_config* cfg, con
   HostRun hr;
   WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
   if (out_labels) {
-    WS_TRY(grow(ctx, ctx->d_out[0], ctx->d_out_cap[0], (hr.npx + 1) / 2));
-    WS_CUDA(ctx, launch_strip_labels(hr.plan->fb.lab, hr.npx, (uint32_t*)ctx->d_out[0], ctx->stream));
-    WS_CUDA(ctx, cudaMemcpyAsync(out_labels, ctx->d_out[0], hr.npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    hr.plan->stats[4] += 1;
+    if (hr.npx * 4 >= ((size_t)1 << 20) && !host_ptr_is_pinned(out_labels)) {
+      // pageable: the label words cross as they are, the workers drop the marker bit out of the ring
+      WS_TRY(staged_d2h(ctx, hr.plan->fb.lab, hr.npx * 4, [=](const uint8_t* sp, size_t off, size_t len) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(sp);
+        uint32_t* dst = out_labels + off / 4;
+        for (size_t i = 0; i < len / 4; ++i) dst[i] = src[i] & LAB_MASK;
+      }));
+    } else {
+      WS_TRY(grow(ctx, ctx->d_out[0], ctx->d_out_cap[0], (hr.npx + 1) / 2));
+      WS_CUDA(ctx, launch_strip_labels(hr.plan->fb.lab, hr.npx, (uint32_t*)ctx->d_out[0], ctx->stream));
+      WS_CUDA(ctx, cudaMemcpyAsync(out_labels, ctx->d_out[0], hr.npx * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      hr.plan->stats[4] += 1;
+    }
   }
-  if (out_level)
-    WS_CUDA(ctx, cudaMemcpyAsync(out_level, hr.plan->fb.lvl, hr.npx, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_level) WS_TRY(copy_d2h(ctx, out_level, hr.plan->fb.lvl, hr.npx));
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return WS_OK;
 }
@@ -1341,21 +1535,7 @@ extern "C" ws_status ws_transform_batch(ws_ctx* ctx, const ws_config* cfg, const
   ws_plan* p = hr.plan;
   cudaStream_t s = ctx->stream;
   const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
-  if (out_labels) {
-    for (size_t b = 0; b < n_img; ++b) {
-      const int buf = (int)(b & 1);
-      WS_TRY(grow(ctx, ctx->d_out[buf], ctx->d_out_cap[buf], hr.npx));
-      if (b >= 2) WS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_copied[buf], 0));
-      WS_CUDA(ctx, launch_widen_labels(p->fb.lab + b * hr.npx, hr.npx, ctx->d_out[buf], s));
-      WS_CUDA(ctx, cudaEventRecord(ctx->ev_ready[buf], s));
-      WS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[buf], 0));
-      WS_CUDA(ctx, cudaMemcpyAsync(out_labels + b * hr.npx, ctx->d_out[buf], hr.npx * 8, cudaMemcpyDeviceToHost,
-                                   ctx->copy_stream));
-      WS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
-      p->stats[4] += 1;
-    }
-    WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-  }
+  if (out_labels) WS_TRY(download_labels_u64(ctx, p, p->fb.lab, n_img * hr.npx, out_labels));
   if (out_lake_counts) {
     std::vector<uint32_t> h(n_img * 256);
     WS_CUDA(ctx, cudaMemcpyAsync(h.data(), p->mb.counts, n_img * 256 * 4, cudaMemcpyDeviceToHost, s));

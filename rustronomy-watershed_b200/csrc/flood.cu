@@ -56,9 +56,10 @@ __device__ __forceinline__ bool consumer_sync_or(bool pred) {
 // state initialisation
 // ---------------------------------------------------------------------------
 
-// T = "never", labels = uncoloured, and the image re-encoded for the flood: a pixel that can
-// never flood -- not a window centre (lib.rs:220), above the last water level (filter (1),
-// lib.rs:224, over levels 0..=max), or padding -- is stored as 255.
+// T = "never" and the image re-encoded for the flood: a pixel that can never flood -- not a window centre
+// (lib.rs:220), above the last water level (filter (1), lib.rs:224, over levels 0..=max), or padding -- is
+// stored as 255.  The label plane is NOT cleared: label_tile writes every word of it, and the only words read
+// before that are the seeds' own (written by seed_init).
 __global__ void __launch_bounds__(256) fill_state_kernel(FloodBuffers b, ImageDims d, const uint8_t* __restrict__ img,
                                                          uint32_t lmax) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -68,11 +69,6 @@ __global__ void __launch_bounds__(256) fill_state_kernel(FloodBuffers b, ImageDi
   const uint4 inf4 = make_uint4(T_INF, T_INF, T_INF, T_INF);
   uint4* T4 = reinterpret_cast<uint4*>(b.T);
   for (size_t i = tid; i < nt4; i += stride) __stcg(T4 + i, inf4);
-  // labels
-  const size_t nl = d.px_total(), nl4 = nl / 4;
-  uint4* L4 = reinterpret_cast<uint4*>(b.lab);
-  for (size_t i = tid; i < nl4; i += stride) __stcg(L4 + i, make_uint4(0u, 0u, 0u, 0u));
-  for (size_t i = nl4 * 4 + tid; i < nl; i += stride) b.lab[i] = 0u;
   // image bytes, four per thread (the padded rows are multiples of 64 bytes)
   const size_t pp = d.pix_plane();
   const int ppitch = d.pix_pitch();
@@ -111,6 +107,7 @@ cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, u
   return cudaMemsetAsync(b.ctrl, 0, sizeof(uint32_t) * FC_WORDS, s);
 }
 
+constexpr uint32_t TILE_NONE_U = 0xFFFFFFFFu;
 __device__ __forceinline__ unsigned long long ld_cg64(const unsigned long long* p) { return __ldcg(p); }
 
 __device__ __forceinline__ uint32_t flood_bucket(uint32_t level, int shift) {
@@ -162,45 +159,86 @@ __device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t tile, 
   }
 }
 
-// Colour the starting pixels (lib.rs:1365-1367): T = 0, colour = index + 1, a later
-// duplicate overwrites an earlier one (sequential loop) == the largest index wins.
+// Colour the starting pixels (lib.rs:1365-1367): T = 0, colour = index + 1, a later duplicate overwrites an
+// earlier one (sequential loop) == the largest index wins.  The label plane is not cleared beforehand, so the
+// colour is a plain store; a position that occurs twice shows up as an exchange on T that returns 0, and
+// only then seed_dup_kernel settles the largest index with atomicMax (every word it touches already holds
+// the colour of one of the duplicates).
 __global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDims d,
                                                         const uint32_t* __restrict__ seeds_rc,
                                                         const uint32_t* __restrict__ seed_off, uint32_t nseeds,
                                                         uint32_t colour_base) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nseeds) return;
-  int lo = 0, hi = d.n_img;  // slice of seed i: last b with seed_off[b] <= i
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
-  }
-  const int img = lo;
-  const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
-  if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) {
-    atomicOr(&b.ctrl[FC_ERROR], 1u);
-    return;
-  }
-  st_cg(&b.T[(size_t)img * d.t_plane() + d.t_index((int)r, (int)c)], 0u);
-  atomicMax(&b.lab[(size_t)img * d.px_per_img() + (size_t)r * d.cols + c],
+  uint32_t tile = TILE_NONE_U, par = 0;
+  uint32_t r = 0, c = 0;
+  int ty = 0, tx = 0;
+  if (i < nseeds) {
+    int lo = 0, hi = d.n_img;  // slice of seed i: last b with seed_off[b] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    const int img = lo;
+    const uint2 rc = __ldg(reinterpret_cast<const uint2*>(seeds_rc) + i);
+    r = rc.x;
+    c = rc.y;
+    if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) {
+      atomicOr(&b.ctrl[FC_ERROR], 1u);
+    } else {
+      const uint32_t old = atomicExch(&b.T[(size_t)img * d.t_plane() + d.t_index((int)r, (int)c)], 0u);
+      st_cg(&b.lab[(size_t)img * d.px_per_img() + (size_t)r * d.cols + c],
             LAB_RESOLVED | (colour_base + i - __ldg(seed_off + img) + 1u));
-  // Red-black order over the tiles: the even tiles (tx + ty even) start in bucket 0, the odd ones in
-  // bucket 1 -- they then already see their neighbours' results, a Gauss-Seidel step at tile level that
-  // saves re-activations.
-  const int ty = r / TILE_H, tx = c / TILE_W;
-  const uint32_t tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
-  const uint32_t par = (uint32_t)(tx + ty) & 1u;
-  push_tile<true>(b, tile, par);  // (the flood is a later launch: no fence needed here)
-  if (r % TILE_H == 0 && ty > 0) push_tile<true>(b, tile - d.tiles_x, par ^ 1u);
-  if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile<true>(b, tile + d.tiles_x, par ^ 1u);
-  if (c % TILE_W == 0 && tx > 0) push_tile<true>(b, tile - 1, par ^ 1u);
-  if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile<true>(b, tile + 1, par ^ 1u);
+      if (old == 0u) st_cg(&b.ctrl[FC_SEED_DUP], 1u);
+      ty = r / TILE_H;
+      tx = c / TILE_W;
+      tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
+      // Red-black order over the tiles: the even tiles (tx + ty even) start in bucket 0, the odd ones in
+      // bucket 1 -- they then already see their neighbours' results, a Gauss-Seidel step at tile level that
+      // saves re-activations.
+      par = (uint32_t)(tx + ty) & 1u;
+    }
+  }
+  // Seeds arrive in row-major order (find_local_minima), so the 32 seeds of a warp share a handful of tiles:
+  // one lane per distinct tile queues it.  (the flood is a later launch: no fence needed here)
+  const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+  if (tile != TILE_NONE_U) {
+    if ((int)(__ffs((int)peers) - 1) == (int)(threadIdx.x & 31)) push_tile<true>(b, tile, par);
+    // a seed on the tile's edge is in the halo of the neighbouring tile: that tile must look as well
+    if (r % TILE_H == 0 && ty > 0) push_tile<true>(b, tile - d.tiles_x, par ^ 1u);
+    if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile<true>(b, tile + d.tiles_x, par ^ 1u);
+    if (c % TILE_W == 0 && tx > 0) push_tile<true>(b, tile - 1, par ^ 1u);
+    if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile<true>(b, tile + 1, par ^ 1u);
+  }
+}
+
+// Only when seed_init saw a position twice: the largest index wins (lib.rs:1365-1367 is a sequential loop).
+__global__ void __launch_bounds__(256) seed_dup_kernel(FloodBuffers b, ImageDims d,
+                                                       const uint32_t* __restrict__ seeds_rc,
+                                                       const uint32_t* __restrict__ seed_off, uint32_t nseeds,
+                                                       uint32_t colour_base) {
+  if (ld_cg(&b.ctrl[FC_SEED_DUP]) == 0u) return;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nseeds; i += stride) {
+    int lo = 0, hi = d.n_img;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    const uint32_t r = seeds_rc[2 * (size_t)i], c = seeds_rc[2 * (size_t)i + 1];
+    if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) continue;
+    atomicMax(&b.lab[(size_t)lo * d.px_per_img() + (size_t)r * d.cols + c],
+              LAB_RESOLVED | (colour_base + i - __ldg(seed_off + lo) + 1u));
+  }
 }
 
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
                              uint32_t nseeds, uint32_t colour_base, cudaStream_t s) {
   if (nseeds == 0) return cudaSuccess;
   seed_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds, colour_base);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const uint32_t want = (nseeds + 255) / 256;
+  seed_dup_kernel<<<want < 4096u ? want : 4096u, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds, colour_base);
   return cudaGetLastError();
 }
 

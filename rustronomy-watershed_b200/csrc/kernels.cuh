@@ -14,6 +14,7 @@ enum FloodCtrl {
   FC_IDLE = 3,         // idle polls of the producer warps
   FC_WAIT_KCYC = 4,    // consumers: kilo-cycles waiting for a staged tile (tail at the end of the flood excluded)
   FC_BUSY_KCYC = 5,    // consumers: kilo-cycles iterating
+  FC_SEED_DUP = 7,     // seed_init saw a seed position twice (the statistics words 0..7 are reset per launch)
   FC_ERROR = 8,        // bit 0: seed out of bounds, bit 1: hop overflow, bit 2: orphan pixel, bit 3: slot never written,
                        // bit 4: flood watchdog, bit 5: a ring slot was overwritten while still in use
   FC_JUMP_FLAG0 = 9,   // [9..11] rotating "still unresolved" flags of the pointer jumping

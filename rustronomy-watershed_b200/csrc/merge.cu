@@ -7,17 +7,21 @@
 // put an edge (a, b) of weight w = max(level(p), level(q)) into the basin graph G, and the lakes at
 // level L are the components of the edges with w <= L, so
 //     lakes(L) = colours on the canvas - (edges of a minimum spanning forest of G with w <= L).
-// Every CTA takes ONE 64x32 tile (plus the pixels right of / below it) and does two things in shared
-// memory, Boruvka-style, under the total edge order (w, tile, edge id in the tile):
-//   1. CONTRACTION.  A basin none of whose pixels touches the tile's rim is *closed*: all its edges
-//      are in this tile.  The lightest edge leaving a component made of closed basins only is the
-//      lightest edge leaving it in the WHOLE graph, hence a forest edge for good (cut property).  It is
-//      emitted as FINAL and only counted; the component is merged into its neighbour.  Open basins
-//      never pick, so a contracted component holds at most one open basin, which stays its root: the
-//      component's identity in every other tile is simply that basin's colour.
-//   2. REDUCTION.  Among the contracted components (all open now) only a spanning forest of the
-//      tile's remaining edges can matter (cycle property); those edges are emitted as DEFERRED, between
-//      the components' open basins, and go through the global level-ordered union-find.
+// Every CTA takes ONE 64x32 tile (plus the pixels right of / below it) and runs Boruvka on the tile's basin
+// graph in shared memory, under the total edge order (w, edge id in the tile); every component picks its
+// lightest edge in every round, and a picked edge is classified by who picked it:
+//   FINAL.  A basin none of whose pixels touches the tile's rim is *closed*: all its edges are in this
+//      tile.  The lightest edge leaving a component made of closed basins only is the lightest edge
+//      leaving it in the WHOLE graph, hence a forest edge for good (cut property).  It is only counted.
+//      The set of basins joined by FINAL edges holds at most one open basin (the edge that would join two
+//      sets with an open basin each is picked by an open component); its *identity* -- the open basin, or
+//      the closed basin where the chain of FINAL moves ends -- stands for all its basins in what follows.
+//   DEFERRED.  Every other pick.  Together with the FINAL ones they are a minimum spanning forest of the
+//      tile's graph, and only those can be in the global forest (cycle property); they are emitted between
+//      the identities of their basins and go through the global level-ordered union-find.
+// (Round 1 used to let only closed components pick, then a second Boruvka reduced the rest: 8.9 rounds and
+// 7.4 k edge looks per tile on a noise field; one Boruvka with classified picks needs 5.3 rounds and 4.8 k
+// looks -- 3.2 k after the first round, which needs no liveness test -- for 15 % more DEFERRED edges.)
 // On a noise field ~3/4 of all basins are closed in their tile, so the global pass -- random accesses
 // over tens of millions of colours -- sees a quarter of the graph.  Final edges are kept (flagged) in the
 // same list: the merge tree that per-level representatives need is built from all of them on demand.
@@ -41,8 +45,8 @@ static_assert(MR_WARPS * MR_SEG == MR_HASH, "the edge list reuses the id table's
 struct MergeSmem {
   uint32_t label_of[MR_NODES];   // dense id -> colour
   uint16_t parent[MR_NODES];     // union-find over dense ids; only a root's own thread re-parents it
-  uint8_t flags[MR_NODES + 3];   // dense id, bit 0: the basin has pixels on the tile's rim (open),
-                                 //           bit 1: it went under another component in the contraction stage
+  uint8_t open_[MR_NODES + 3];   // dense id: the basin has pixels on the tile's rim; propagated to the roots
+                                 // (only ever set, so plain byte stores of 1 are race-free)
   union {
     uint32_t table[MR_HASH];     // while dense ids are handed out: 0 = free, else the label / the id
     uint32_t edge[MR_HASH];      // afterwards: 8 warp-private segments of live edges, compacted every round
@@ -52,14 +56,17 @@ struct MergeSmem {
     struct {
       uint32_t best[MR_NODES];   // root: smallest (level << 16 | slot) offered this round; after the id went
                                  // under another component: the edge it went along (an edge word)
-      uint16_t comp[MR_NODES];   // root of every id at the start of the round | open << 15
-      uint16_t rep[MR_NODES];    // root after the contraction stage (the component's open basin)
+      uint16_t comp[MR_NODES];   // root of every id at the start of the round
+      uint16_t link[MR_NODES];   // FINAL moves only: the basin at the far end of the edge (else the id itself);
+                                 // following the links gives the identity of a contracted basin; bit 15: FINAL
     } r;
   } b;
   uint32_t nlab, nout, gpos, first;
 };
 
-// `contract` = 0 skips stage 0 (every edge is emitted DEFERRED).
+// One Boruvka over the tile's basin graph; every component picks its lightest edge in every round.  A pick
+// made by a component that holds closed basins only is FINAL (cut property: all edges of a closed basin lie
+// in this tile), every other pick is DEFERRED.  `contract` = 0 treats every basin as open (no FINAL edges).
 __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t* __restrict__ lab,
                                                                   const uint8_t* __restrict__ lvl, ImageDims d,
                                                                   const uint32_t* __restrict__ seed_off, int contract,
@@ -88,11 +95,11 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
       uint32_t v = 255;
       if (gr < d.rows && gc < d.cols) {
         const size_t p = base + (size_t)gr * d.cols + gc;
-        L[k] = lab[p] & LAB_MASK;
-        v = lvl[p];
+        L[k] = __ldg(lab + p) & LAB_MASK;
+        v = __ldg(lvl + p);
       }
       sm.b.n.lvl[i] = (uint8_t)v;
-      sm.flags[i] = 0;
+      sm.open_[i] = 0;
       sm.parent[i] = (uint16_t)i;
       if (L[k] != 0u && sm.first == 0u) sm.first = L[k];  // any coloured label (benign race)
     }
@@ -108,13 +115,18 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
   }
 
   // (b) dense ids, one per distinct label: insert the labels into an open-addressing table, number the
-  // occupied slots, then replace every slot's label by its id
+  // occupied slots, then replace every slot's label by its id.  Consecutive lanes hold consecutive nodes of
+  // a row, and a basin is a few pixels wide: only the first lane of a run of equal labels probes the table,
+  // the others take its slot by shuffle.
   uint16_t slot[MR_PER_THREAD];
 #pragma unroll
   for (int k = 0; k < MR_PER_THREAD; ++k) {
     const uint32_t l = L[k];
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, l, 1);
+    const bool lead = lane == 0 || prev != l;
+    const uint32_t leaders = __ballot_sync(0xffffffffu, lead);
     uint32_t h = (l * 2654435761u) >> 20;
-    if (l != 0u) {
+    if (lead && l != 0u) {
       for (;;) {
         uint32_t cur = ((volatile uint32_t*)sm.a.table)[h];
         if (cur == 0u) cur = atomicCAS(&sm.a.table[h], 0u, l);
@@ -122,19 +134,34 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
         h = (h + 1u) & (MR_HASH - 1);
       }
     }
-    slot[k] = (uint16_t)h;
+    const int src = 31 - __clz((int)(leaders & (0xFFFFFFFFu >> (31 - lane))));  // my run's first lane
+    slot[k] = (uint16_t)__shfl_sync(0xffffffffu, h, src);
   }
   __syncthreads();
   {
     uint32_t key[MR_HASH / MR_THREADS];
 #pragma unroll
     for (int k = 0; k < MR_HASH / MR_THREADS; ++k) key[k] = sm.a.table[tid + k * MR_THREADS];
+    // ids in blocks: one shared atomic per warp
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < MR_HASH / MR_THREADS; ++k) mine += (key[k] != 0u);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t wbase = 0;
+    if (lane == 31 && incl) wbase = atomicAdd(&sm.nlab, incl);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    uint32_t id = wbase + incl - mine;
 #pragma unroll
     for (int k = 0; k < MR_HASH / MR_THREADS; ++k) {
       if (key[k] == 0u) continue;
-      const uint32_t id = atomicAdd(&sm.nlab, 1u);
       sm.label_of[id] = key[k];
       sm.a.table[tid + k * MR_THREADS] = id;  // (only this thread touches the slot in this phase)
+      ++id;
     }
   }
   __syncthreads();
@@ -153,7 +180,7 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
       const int gr = r0 + r;
       if (!contract || r == TILE_H || c == TILE_W || (r == 0 && r0 > 0) || (c == 0 && c0 > 0) ||
           (d.halo_top && gr <= 1) || (d.halo_bottom && gr == d.rows - 1))
-        sm.flags[id] = 1;
+        sm.open_[id] = 1;
     }
     sm.b.n.lid[i] = (uint16_t)id;
   }
@@ -189,93 +216,95 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     cnt += __popc(m);
   }
   if (!__syncthreads_or(cnt != 0u)) return;  // no edge between different basins in this tile
-  // (lid / lvl are dead from here on: their memory becomes best / comp / rep)
+  // (lid / lvl are dead from here on: their memory becomes best / comp / link)
   for (int i = tid; i < nlab; i += MR_THREADS) {
     sm.b.r.best[i] = MR_NONE;
     sm.b.r.comp[i] = (uint16_t)i;
-    sm.b.r.rep[i] = (uint16_t)i;
+    sm.b.r.link[i] = (uint16_t)i;
   }
   __syncthreads();
 
-  // (d) stage 0: contraction (only components of closed basins pick), stage 1: spanning forest of the rest.
-  // Keys (level << 16 | slot in the edge list) are distinct within a round, so the picks of a round form
-  // a forest apart from mutual picks of one edge, where the larger root goes under the smaller.  (The
-  // order among equal levels may differ from round to round: every round is a valid Boruvka step on the
+  // (d) Boruvka.  Keys (level << 16 | slot in the edge list) are distinct within a round, so the picks of a
+  // round form a forest apart from mutual picks of one edge; of such a pair exactly one side moves: the closed
+  // one if only one is closed (so that an open basin never goes along a FINAL edge), else the larger root.
+  // (The order among equal levels may differ from round to round: every round is a valid Boruvka step on the
   // graph contracted so far.)
-  constexpr uint32_t OPEN = 0x8000u, ROOT = 0x7FFFu;
-  for (int stage = contract ? 0 : 1; stage < 2; ++stage) {
-    const uint32_t picks = stage == 1 ? OPEN : 0u;  // a component picks when (comp & OPEN) <= picks
-    for (;;) {
-      // roots (reads racing with the flattening stores still see an ancestor).  An id that was a root
-      // and went under another component in the previous round keeps the edge it went along.
-      for (int i = tid; i < nlab; i += MR_THREADS) {
-        uint32_t x = (uint32_t)i;
-        for (uint32_t p = sm.parent[x]; p != x; p = sm.parent[x]) x = p;
-        if ((sm.b.r.comp[i] & ROOT) == (uint32_t)i) {
-          if (x != (uint32_t)i) {
-            sm.b.r.best[i] = sm.a.edge[sm.b.r.best[i] & 0xFFFFu];
-            if (stage == 0) sm.flags[i] |= 2;
-          } else {
-            sm.b.r.best[i] = MR_NONE;
-          }
-        }
-        sm.parent[i] = (uint16_t)x;
-        sm.b.r.comp[i] = (uint16_t)(x | ((sm.flags[x] & 1) ? OPEN : 0u));
-      }
-      __syncthreads();
-#ifdef WS_MERGE_STATS  // rounds and edge looks per stage (scripts/merge_stats.py)
-      if (tid == 0) atomicAdd(&red_count[4 + stage], 1u);
-      if (lane == 0) atomicAdd(&red_count[6 + stage], cnt);
+  // Round 1: every basin is its own component and every edge is alive -- offers only.
+  for (uint32_t j = lane; j < cnt; j += 32) {
+    const uint32_t e = seg[j];
+    const uint32_t key = ((e >> 24) << 16) | (uint32_t)(warp * MR_SEG + j);
+    atomicMin(&sm.b.r.best[e & 0xFFFu], key);
+    atomicMin(&sm.b.r.best[(e >> 12) & 0xFFFu], key);
+  }
+  constexpr uint32_t FIN = 0x8000u, IDM = 0x7FFFu;
+  for (;;) {
+    __syncthreads();
+#ifdef WS_MERGE_STATS  // rounds and edge looks (scripts/merge_stats.py)
+    if (tid == 0) atomicAdd(&red_count[4], 1u);
+    if (lane == 0) atomicAdd(&red_count[6], cnt);
 #endif
-      // one pass over my warp's live edges: drop those inside one component, keep the rest compacted,
-      // offer each to the components at its ends
-      bool any = false;
-      uint32_t kept = 0;
-      for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        uint32_t e = 0, cu = 0, cv = 0;
-        if (j < cnt) {
-          e = seg[j];
-          cu = sm.b.r.comp[e & 0xFFFu];
-          cv = sm.b.r.comp[(e >> 12) & 0xFFFu];
-        }
-        const bool alive = cu != cv;
-        const uint32_t m = __ballot_sync(0xffffffffu, alive);  // (also orders this step's reads before its writes)
-        if (alive) {
-          const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
-          seg[pos] = e;
-          const uint32_t key = ((e >> 24) << 16) | (uint32_t)(warp * MR_SEG + pos);
-          const bool pu = (cu & OPEN) <= picks, pv = (cv & OPEN) <= picks;
-          if (pu) atomicMin(&sm.b.r.best[cu & ROOT], key);
-          if (pv) atomicMin(&sm.b.r.best[cv & ROOT], key);
-          any |= pu | pv;
-        }
-        kept += __popc(m);
-      }
-      cnt = kept;
-      if (!__syncthreads_or(any)) break;
-      // every picking root goes under the component at the other end of its edge
-      for (int i = tid; i < nlab; i += MR_THREADS) {
-        if ((sm.b.r.comp[i] & ROOT) != (uint32_t)i) continue;
-        const uint32_t key = sm.b.r.best[i];
-        if (key == MR_NONE) continue;
-        const uint32_t e = sm.a.edge[key & 0xFFFFu];
-        const uint32_t cu = sm.b.r.comp[e & 0xFFFu] & ROOT, cv = sm.b.r.comp[(e >> 12) & 0xFFFu] & ROOT;
-        const uint32_t other = cu == (uint32_t)i ? cv : cu;
-        if (sm.b.r.best[other] == key && (uint32_t)i < other) continue;  // mutual pick: the other one moves
-        sm.parent[i] = (uint16_t)other;
-      }
-      __syncthreads();
+    // every picking root goes under the component at the other end of its edge
+    for (int i = tid; i < nlab; i += MR_THREADS) {
+      if (sm.b.r.comp[i] != (uint16_t)i) continue;
+      const uint32_t key = sm.b.r.best[i];
+      if (key == MR_NONE) continue;
+      const uint32_t e = sm.a.edge[key & 0xFFFFu];
+      const uint32_t ia = e & 0xFFFu, ib = (e >> 12) & 0xFFFu;
+      const uint32_t cu = sm.b.r.comp[ia], cv = sm.b.r.comp[ib];
+      const uint32_t other = cu == (uint32_t)i ? cv : cu;
+      const bool mutual = sm.b.r.best[other] == key;
+      const bool ci = !sm.open_[i], co = !sm.open_[other];  // closed components (open_ of a root is current)
+      if (mutual && (ci == co ? (uint32_t)i < other : !ci)) continue;  // the other one moves
+      sm.parent[i] = (uint16_t)other;
+      if (ci || (mutual && co))  // FINAL; a closed mover takes the identity of the basin at the far end
+        sm.b.r.link[i] = (uint16_t)(FIN | (ci ? (cu == (uint32_t)i ? ib : ia) : (uint32_t)i));
     }
-    if (stage == 0) {  // comp[] is current (no hook since the last flatten): the contracted components
-      for (int i = tid; i < nlab; i += MR_THREADS) sm.b.r.rep[i] = sm.b.r.comp[i] & ROOT;
-      __syncthreads();
+    __syncthreads();
+    // roots (reads racing with the flattening stores still see an ancestor).  An id that was a root and has
+    // just gone under another component keeps the edge it went along (the list is not compacted in between).
+    for (int i = tid; i < nlab; i += MR_THREADS) {
+      uint32_t x = (uint32_t)i;
+      for (uint32_t p = sm.parent[x]; p != x; p = sm.parent[x]) x = p;
+      if (sm.b.r.comp[i] == (uint16_t)i) {
+        if (x != (uint32_t)i) sm.b.r.best[i] = sm.a.edge[sm.b.r.best[i] & 0xFFFFu];
+        else sm.b.r.best[i] = MR_NONE;
+      }
+      sm.parent[i] = (uint16_t)x;
+      sm.b.r.comp[i] = (uint16_t)x;
+      if (x != (uint32_t)i && sm.open_[i]) sm.open_[x] = 1;
     }
+    __syncthreads();
+    // one pass over my warp's live edges: drop those inside one component, keep the rest compacted,
+    // offer each to the components at its ends
+    bool any = false;
+    uint32_t kept = 0;
+    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      uint32_t e = 0, cu = 0, cv = 0;
+      if (j < cnt) {
+        e = seg[j];
+        cu = sm.b.r.comp[e & 0xFFFu];
+        cv = sm.b.r.comp[(e >> 12) & 0xFFFu];
+      }
+      const bool alive = cu != cv;
+      const uint32_t m = __ballot_sync(0xffffffffu, alive);  // (also orders this step's reads before its writes)
+      if (alive) {
+        const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
+        seg[pos] = e;
+        const uint32_t key = ((e >> 24) << 16) | (uint32_t)(warp * MR_SEG + pos);
+        atomicMin(&sm.b.r.best[cu], key);
+        atomicMin(&sm.b.r.best[cv], key);
+        any = true;
+      }
+      kept += __popc(m);
+    }
+    cnt = kept;
+    if (!__syncthreads_or(any)) break;
   }
 
   // (e) every id that is not a root went under another component along exactly one edge: append those
   // edges to the global list as global colour ids -- FINAL edges (bit 31 of .y) between the two basins
-  // themselves, DEFERRED ones between the open basins of the contracted components
+  // themselves, DEFERRED ones between the identities of the two basins (the end of their chains of FINAL moves)
   uint32_t mine = 0;
   if (tid == 0) sm.first = 0;  // from here on: cursor into this tile's part of the global list
   for (int i = tid; i < nlab; i += MR_THREADS) mine += (sm.parent[i] != (uint16_t)i);
@@ -293,9 +322,14 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
   for (int i = tid; i < nlab; i += MR_THREADS) {
     if (sm.parent[i] == (uint16_t)i) continue;
     const uint32_t e = sm.b.r.best[i];
-    const uint32_t fin = (sm.flags[i] >> 1) & 1u;
+    const uint32_t fin = (sm.b.r.link[i] & FIN) ? 1u : 0u;
     uint32_t ia = e & 0xFFFu, ib = (e >> 12) & 0xFFFu;
-    if (!fin && contract) { ia = sm.b.r.rep[ia]; ib = sm.b.r.rep[ib]; }
+    if (!fin) {  // (read-only walks: no link changes any more; chains of FINAL moves are acyclic -- the bound
+                 // only keeps a broken invariant from hanging the device)
+      int guard = nlab;
+      for (uint32_t l = sm.b.r.link[ia] & IDM; l != ia && guard > 0; l = sm.b.r.link[ia] & IDM, --guard) ia = l;
+      for (uint32_t l = sm.b.r.link[ib] & IDM; l != ib && guard > 0; l = sm.b.r.link[ib] & IDM, --guard) ib = l;
+    }
     red_ab[at] = make_uint2(gbase + sm.label_of[ia], (gbase + sm.label_of[ib]) | (fin << 31));
     red_w[at] = (uint8_t)(e >> 24);
     ++at;
