@@ -121,11 +121,13 @@ class ClockSampler:
 # CPU legs (the only places bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------
 
-def cpu_sample(field: str, size: int, crop: int, seed: int):
-    """The oracle on a crop of the same workload: both transforms, all host threads, with the
-    reference's own closure (literal make_colour_map).  Returns (Mpx*levels/s, seconds, threads)."""
+def cpu_sample(field: str, size: int, crop: int, seed: int, threads: int = 0):
+    """The oracle on a crop of the same workload: both transforms, with the reference's own closure (literal
+    make_colour_map).  threads = 0: every CPU this process may run on, set explicitly (torchrun exports
+    OMP_NUM_THREADS=1, which is not the reference's rayon default).  Returns (Mpx*levels/s, seconds, threads)."""
     from oracle import oracle as orc
     orc.build()
+    orc.set_num_threads(threads if threads > 0 else len(os.sched_getaffinity(0)))
     img = make_field(field, size, seed)[:crop, :crop].copy() if size <= 4096 else make_field(field, crop, seed)
     seeds = orc.find_local_minima(img)
     t0 = time.perf_counter()
@@ -150,8 +152,9 @@ def reference_arm(args, rank: int):
         v, dt, threads = cpu_sample(args.field, args.size, crop, s)
         vals.append(v)
         secs.append(dt)
-    total = time.perf_counter() - t_all
     value = args.steps * 2 * crop * crop * LEVELS / sum(secs) / 1e6
+    one_v, one_dt, _ = cpu_sample(args.field, args.size, crop, 0, threads=1)   # tests/core_bench.rs:40-51 also times 1 thread
+    total = time.perf_counter() - t_all
     sample = (f"{crop}x{crop} {args.field} field per step (bounded sample of the {args.size}x{args.size} workload), "
               "segmenting + merging, literal make_colour_map")
     line = {
@@ -161,7 +164,8 @@ def reference_arm(args, rank: int):
         "data": "synthetic",
         "config": {"workload": f"{args.size}x{args.size} u8 {args.field} field, segmenting + merging, 255 levels",
                    "cpu_sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "value_1_thread": one_v, "seconds_1_thread": one_dt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": total,
     }
@@ -172,6 +176,17 @@ def reference_arm(args, rank: int):
 # ---------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------
+
+class _DevArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def dev_view(ptr: int, shape, typestr: str):
+    """A torch view of device memory owned by the library."""
+    import torch
+    return torch.as_tensor(_DevArray(ptr, shape, typestr), device="cuda")
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -185,6 +200,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra smooth-field measurement")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-checksum", action="store_true")
+    ap.add_argument("--no-strips", action="store_true", help="N > 1: skip the row-strip run of one field (config 4)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -250,8 +267,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def checksum():
+        """Order-dependent 64-bit checksums of the arrival times, labels, levels and lake counts the plan holds."""
+        out = []
+        for ptr, ts in ((plan.arrival_times_ptr, "<i4"), (plan.labels_ptr, "<i4"), (plan.levels_ptr, "|u1")):
+            v = dev_view(ptr, (npx,), ts)
+            acc = 0
+            for lo in range(0, npx, 1 << 26):                      # 64 M elements at a time (bounded temporaries)
+                x = v[lo:lo + (1 << 26)].to(torch.int64)
+                k = torch.arange(lo, lo + x.numel(), device="cuda", dtype=torch.int64) % 1000003 + 1
+                acc = (acc + int((x * k).sum().item())) & 0xFFFFFFFFFFFFFFFF
+            out.append(acc)
+        out.append(int(dev_view(plan.lake_counts_ptr, (256,), "<i4").to(torch.int64).sum().item()))
+        return out
+
     for _ in range(args.warmup):
         step()
+    sums_warm = checksum() if not args.no_checksum else None
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -266,6 +298,15 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
+    # the asynchronous flood takes a different schedule every time: the results of the last timed step must be the
+    # bytes of the warm-up steps (checked outside the timed region)
+    determinism = None
+    if sums_warm is not None:
+        sums_last = checksum()
+        determinism = {"what": "checksums of arrival times, labels, levels, lake counts: last warm-up step vs last timed step",
+                       "identical": sums_warm == sums_last}
+        if sums_warm != sums_last:
+            print(f"DETERMINISM FAILURE: {sums_warm} != {sums_last}", file=sys.stderr)
     stats = plan.stats()
     if world > 1:
         t = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
@@ -307,43 +348,134 @@ def main():
         plan.find_local_minima(d_img.data_ptr(), d_seeds.data_ptr(), nseeds, d_off.data_ptr())
         del simg, sseeds
 
-    # ---- end to end through the reference-facing API, host buffers (pinned) --------------
+    # ---- extra at N > 1 (BASELINE config 4): ONE S x S field as row strips, one strip per GPU ----------
+    # NCCL halo exchange on the library's stream + boundary forest (strips.py); the field is rank 0's field of
+    # the run above, so the strips are compared bit for bit with rank 0's single-GPU result.
+    extra_strips = None
+    if world > 1 and not args.no_strips and args.field == "uniform" and S % world == 0:
+        import importlib
+        st = importlib.import_module("rustronomy_watershed_b200.strips")
+        whole = img_h.numpy() if rank == 0 else make_field(args.field, S, seed=0)
+        parts = st.partition_rows(S, world)
+        g = st.StripGeometry(rank, world, S, parts[rank])
+        lo, hi = g.local_rows
+        strip = st.CudaStrip(ws, ctx, g, torch.from_numpy(np.ascontiguousarray(whole[lo:hi])).cuda())
+        comm = st.DistComm()
+        comm.set_device(torch.device("cuda", local_rank))
+        times, res = [], None
+        for rep in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            res = st.solve([strip], comm, st.MERGING, 254)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if rep:
+                times.append(1e3 * float(dt.item()))
+        own = slice(1 if g.halo_top else 0, strip.rows - (1 if g.halo_bottom else 0))
+        lab = dev_view(strip.plan.labels_ptr, (strip.rows, S), "<i4")[own].contiguous() & 0x7FFFFFFF
+        lvl = dev_view(strip.plan.levels_ptr, (strip.rows, S), "|u1")[own].contiguous()
+        all_lab = torch.empty((S, S), dtype=torch.int32, device="cuda")
+        all_lvl = torch.empty((S, S), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(all_lab, lab)
+        dist.all_gather_into_tensor(all_lvl, lvl)
+        exact = None
+        if rank == 0:      # the single-GPU merging run of this very field
+            plan.run(1, 254, d_img.data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), nseeds)
+            ref_lab = dev_view(plan.labels_ptr, (S, S), "<i4") & 0x7FFFFFFF
+            ref_lvl = dev_view(plan.levels_ptr, (S, S), "|u1")
+            ref_lakes = dev_view(plan.lake_counts_ptr, (256,), "<i4").cpu().numpy()[:255]
+            exact = bool(torch.equal(all_lab, ref_lab)) and bool(torch.equal(all_lvl, ref_lvl)) and \
+                bool(np.array_equal(ref_lakes.astype(np.int64), res.lake_counts.astype(np.int64)))
+        extra_strips = {"workload": f"ONE {S}x{S} u8 {args.field} field, merging transform, {world} row strips (one per GPU), "
+                                    "NCCL halo exchange + boundary forest", "ms": min(times), "ms_all": times,
+                        "single_gpu_merging_ms": sum(phases[1].values()), "flood_exchange_rounds": res.flood_rounds,
+                        "label_exchange_rounds": res.label_rounds, "bit_exact_vs_single_gpu": exact,
+                        "value": npx * LEVELS / (min(times) * 1e-3) / 1e6, "unit": UNIT, "scaling": "strong",
+                        "phase_ms_rank0": {k: round(1e3 * v, 3) for k, v in (res.phase_s or {}).items()}}
+        del all_lab, all_lvl, lab, lvl
+        strip.close()
+        torch.cuda.empty_cache()
+
+    # ---- end to end through the reference-facing API, HOST buffers -----------------------------------
+    # Headline: ordinary (pageable) numpy arrays, which is what a Rust caller's ArrayView2<u8>, &[(usize, usize)]
+    # and Array2<usize> are; the library stages them through its page-locked ring with its worker threads.
+    # Beside it: page-locked caller buffers (direct copies), and the optional ways to move fewer bytes.
     e2e = None
     if not args.no_e2e:
         seg = ws.TransformBuilder.default().set_device(local_rank).build_segmenting()
         mrg = ws.TransformBuilder.default().set_device(local_rank).build_merging()
-        img_np = img_h.numpy()
+        hctx = seg._ctx()
+        host_threads = max(1, min(16, len(all_cpus) // max(world, 1)))
+        hctx.set_host_threads(host_threads)            # the ranks of one box share its cores
+        img_pin = img_h.numpy()
         seeds_h = torch.empty((max(nseeds, 1), 2), dtype=torch.int64).pin_memory()
         seeds_h.copy_(d_seeds.cpu().to(torch.int64) & 0xFFFFFFFF)
-        seeds_np = seeds_h.numpy().view(np.uint64)[:nseeds]
+        seeds_pin = seeds_h.numpy().view(np.uint64)[:nseeds]
         out_h = torch.empty((S, S), dtype=torch.int64).pin_memory()
-        out_np = out_h.numpy().view(np.uint64)
+        out_pin = out_h.numpy().view(np.uint64)
+        img_pg, seeds_pg = img_pin.copy(), seeds_pin.copy()       # pageable copies of the same bytes
+        out_pg = np.zeros((S, S), dtype=np.uint64)                # (touched once: page faults are not the engine's)
         plan.close()                                   # the host-level calls bring their own workspace
         del d_seeds, d_img
         torch.cuda.empty_cache()
 
-        def e2e_step():
-            seg.transform(img_np, seeds_np, out=out_np)          # H2D image+seeds, D2H u64 labels
-            return mrg.lake_counts(img_np, seeds_np)             # H2D image+seeds, D2H per-level counts
+        def run_variant(fn):
+            for _ in range(min(args.warmup, 2)):
+                res = fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                res = fn()
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return 1e3 * dt / args.steps, res
 
-        for _ in range(min(args.warmup, 2)):
-            lakes, unc = e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            lakes, unc = e2e_step()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        h2d = 2 * (npx + nseeds * 16)                  # image + (usize, usize) seed pairs as the API takes them, both transforms
-        d2h = npx * 8 + 2 * LEVELS * 4 + 1024          # u64 labels + counts + level histogram
-        e2e = {"value": world * args.steps * px_levels_step / e2e_s / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-               "api": "SegmentingWatershed.transform + MergingWatershed.lake_counts (ws_transform, "
-                      "ws_transform_lake_counts), pinned host buffers",
+        def step_pageable():
+            seg.transform(img_pg, seeds_pg, out=out_pg)          # H2D image + seeds (narrowed on the way), D2H labels
+            return mrg.lake_counts(img_pg, seeds_pg)             # H2D image + seeds, D2H per-level counts
+
+        def step_pinned():
+            seg.transform(img_pin, seeds_pin, out=out_pin)
+            return mrg.lake_counts(img_pin, seeds_pin)
+
+        def step_auto():
+            seg.transform(img_pg, None, out=out_pg)              # seeds = find_local_minima(image) on the device
+            return mrg.lake_counts(img_pg, None)
+
+        def step_compact():
+            seg.transform_compact(img_pg, seeds_pg)              # u32 labels + u8 levels (allocates its outputs)
+            return mrg.lake_counts(img_pg, seeds_pg)
+
+        ms_pg, (lakes, unc) = run_variant(step_pageable)
+        check_pg = int(out_pg[::97, ::89].sum())
+        ms_pin, (lakes2, _) = run_variant(step_pinned)
+        same = bool(np.array_equal(lakes, lakes2)) and check_pg == int(out_pin[::97, ::89].sum())
+        hctx.set_option(ws._native.WS_OPT_PINNED_HOST_WIDEN, 1)
+        ms_pin_hw, _ = run_variant(step_pinned)
+        hctx.set_option(ws._native.WS_OPT_PINNED_HOST_WIDEN, 0)
+        ms_auto, (lakes3, _) = run_variant(step_auto)
+        same = same and bool(np.array_equal(lakes, lakes3)) and check_pg == int(out_pg[::97, ::89].sum())
+        ms_compact, _ = run_variant(step_compact)
+        seeds_up = nseeds * 8                              # u32 pairs on the link (narrowed by the host threads)
+        h2d = 2 * (npx + seeds_up)
+        d2h = npx * 4 + 2 * LEVELS * 4 + 1024              # u32 label words, widened out of the ring + counts + histogram
+        e2e = {"value": world * px_levels_step / (ms_pg * 1e-3) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_pg,
+               "host_memory": "pageable", "host_threads": host_threads,
+               "api": "SegmentingWatershed.transform -> usize labels + MergingWatershed.lake_counts (ws_transform, "
+                      "ws_transform_lake_counts), ordinary numpy arrays in and out; caller-side bytes: "
+                      f"{2 * (npx + nseeds * 16)} in, {npx * 8} out",
+               "variants_ms_per_step": {
+                   "pinned_caller_buffers (usize seeds + usize labels on the link)": ms_pin,
+                   "pinned_caller_buffers, labels widened by host threads": ms_pin_hw,
+                   "pageable, seeds found on the device (WS_SEEDS_AUTO)": ms_auto,
+                   "pageable, compact outputs (u32 labels + u8 levels, ws_transform_compact)": ms_compact},
+               "variants_agree": same,
                "lakes_first_last": [int(lakes[0]), int(lakes[-1])]}
 
     if rank != 0:
@@ -380,7 +512,8 @@ def main():
     if world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, all_cpus)              # the CPU baseline gets every core the box gives us
         v, dt, thr = cpu_sample(args.field, S, args.cpu_crop, 0)
-        cpu = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
+        v1, dt1, _ = cpu_sample(args.field, S, min(args.cpu_crop, 512), 0, threads=1)
+        cpu = {"value": v, "unit": UNIT, "cores": thr, "kind": "port", "value_1_thread": v1,
                "sample": f"{args.cpu_crop}x{args.cpu_crop} {args.field} crop, segmenting + merging, {dt:.1f} s; "
                          "CPU restatement of the reference algorithm (no Rust toolchain in the image)"}
 
@@ -394,7 +527,7 @@ def main():
                    "parallelism": f"{world} independent fields (shards, no collective)", "host_binding": numa},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
         "phases_ms_last_step": {"segmenting": phases[0], "merging": phases[1]},
-        "extra_smooth_field": extra,
+        "extra_smooth_field": extra, "extra_strips": extra_strips, "determinism": determinism,
         "counters_last_run": stats,
     }
     print(json.dumps(line))

@@ -98,6 +98,25 @@ void ws_free(void *p);
 /* Key of the WS_TIE_RANDOM generator (default: drawn from the OS when the ctx is made, like thread_rng). */
 ws_status ws_ctx_set_tie_seed(ws_ctx *ctx, uint64_t seed);
 
+/* Host threads of this ctx that move PAGEABLE caller memory (an ordinary Array2 / Vec) through a page-locked
+ * ring while the copy engines run, and do the format changes of the boundary on the way (usize <-> u32).
+ * 0 = default: min(16, CPUs this process may run on), or the environment variable WS_HOST_THREADS.
+ * Page-locked caller memory is copied directly and needs no host thread.                              */
+ws_status ws_ctx_set_host_threads(ws_ctx *ctx, int nthreads);
+typedef enum ws_option {
+  /* usize label outputs in PAGE-LOCKED caller memory: 0 (default) = widened on the device, 8 bytes per pixel
+   * over the link, no host work; 1 = 4 bytes per pixel over the link, widened by the host threads (what
+   * pageable destinations always get).                                                                */
+  WS_OPT_PINNED_HOST_WIDEN = 1
+} ws_option;
+ws_status ws_ctx_set_option(ws_ctx *ctx, ws_option opt, int value);
+
+/* Pass as `nseeds` (with seeds_rc == NULL) to the transforms below: the starting points are
+ * WatershedUtils::find_local_minima(image) (lib.rs:1178-1197), found on the device, so that only the image
+ * crosses the link -- what `transform(img, &find_local_minima(img))` of the README computes.  Not available
+ * with edge correction (the reference's caller finds the seeds on the unpadded image, lib.rs:1365-1367).  */
+#define WS_SEEDS_AUTO ((size_t)-1)
+
 /* ---- TransformBuilder::build_segmenting / build_merging (lib.rs:998-1046) -- */
 /* Only the validation is left to do: 1 <= max_water_level <= 254.             */
 ws_status ws_config_validate(const ws_config *cfg);
@@ -307,6 +326,38 @@ ws_status ws_plan_strip_edges(ws_plan *plan, const void **d_ab, const void **d_w
 /* Kruskal over an edge list gathered from all strips: fills ws_plan_lake_counts()[0..255].      */
 ws_status ws_plan_union_edges(ws_plan *plan, const void *d_ab, const void *d_w, size_t n,
                               size_t ncolours, uint32_t ndistinct, uint8_t max_water_level);
+
+/* The same steps without any host synchronisation, for drivers that keep several exchange rounds in flight
+ * (strips.py: NCCL on the library's stream): everything is enqueued on ws_ctx_stream(), the `changed` /
+ * `pending` results are accumulated into device words of the caller (*d_changed |= 1, *d_pending += n), and
+ * errors are collected by ws_plan_strip_check(), the only call that waits.                                  */
+ws_status ws_plan_strip_begin_async(ws_plan *plan, const ws_config *cfg, const ws_strip *strip,
+                                    const uint8_t *d_img, const uint32_t *d_seeds_rc, size_t nseeds);
+ws_status ws_plan_strip_export_times_async(ws_plan *plan, uint32_t *d_top, uint32_t *d_bottom);
+ws_status ws_plan_strip_import_times_async(ws_plan *plan, const uint32_t *d_top, const uint32_t *d_bottom,
+                                           uint32_t *d_changed);
+ws_status ws_plan_strip_labels_async(ws_plan *plan);
+ws_status ws_plan_strip_export_labels_async(ws_plan *plan, uint32_t *d_top, uint32_t *d_bottom);
+ws_status ws_plan_strip_import_labels_async(ws_plan *plan, const uint32_t *d_top, const uint32_t *d_bottom,
+                                            uint32_t *d_pending);
+/* (between the asynchronous label rounds only the compact rim array is resolved; this finishes the label
+ * plane once the rounds are over -- before ws_plan_labels() is read or ws_plan_strip_forest() runs)      */
+ws_status ws_plan_strip_labels_finish_async(ws_plan *plan);
+ws_status ws_plan_strip_check(ws_plan *plan);
+/* Merging over strips without gathering the strips' edge lists ("boundary union-merge").
+ * Every strip reduces its own basin graph to (a) the number of certain forest edges per level and (b) the few
+ * forest edges between basins that touch its boundary rows -- at most one per such basin -- and writes both
+ * into one device-resident packet of ws_strip_packet_bytes(cols) bytes:
+ *   uint32 header[260] = { edges, colours present, error bits, rounds, FINAL edges per level [256] },
+ *   then cap = (3 * cols + 64 rounded up to 16) pairs (colour a - 1, colour b - 1) of uint32, then cap level bytes.
+ * The driver all-gathers the packets (a few hundred KB each) and hands them, back to back, to
+ * ws_plan_forest_packets on any plan of the same width, which leaves the lakes per level of the whole field
+ * in ws_plan_lake_counts().  Nothing synchronises; ws_plan_strip_check() reports errors.
+ * ncolours_total = number of seeds of the whole field (colours are global: colour_base + i + 1).           */
+size_t ws_strip_packet_bytes(size_t cols);
+ws_status ws_plan_strip_forest(ws_plan *plan, size_t ncolours_total, void *d_packet);
+ws_status ws_plan_forest_packets(ws_plan *plan, const void *d_packets, size_t n_packets,
+                                 size_t ncolours_total, uint8_t max_water_level);
 
 /* CUDA-event durations (ms) of the phases of the last run, measured on the ctx stream:
  * [0] state fill + seed colouring, [1] flood kernel, [2] parent + pointer jumping,

@@ -23,6 +23,8 @@ STATUS_NAMES = {
 WS_ERR_MAX_TOO_HIGH, WS_ERR_MAX_TOO_LOW, WS_ERR_SEED_OOB, WS_ERR_NO_DEVICE = 2, 3, 4, 5
 WS_SEGMENTING, WS_MERGING = 0, 1
 WS_TIE_FIRST, WS_TIE_RANDOM = 0, 1
+WS_SEEDS_AUTO = C.c_size_t(-1).value          # nseeds: find_local_minima(image) on the device
+WS_OPT_PINNED_HOST_WIDEN = 1
 
 
 class WsConfig(C.Structure):
@@ -59,6 +61,8 @@ SIGNATURES = {
     "ws_abi_version": (C.c_int, []),
     "ws_free": (None, [_P]),
     "ws_ctx_set_tie_seed": (C.c_int, [_P, C.c_uint64]),
+    "ws_ctx_set_host_threads": (C.c_int, [_P, C.c_int]),
+    "ws_ctx_set_option": (C.c_int, [_P, C.c_int, C.c_int]),
     "ws_config_validate": (C.c_int, [C.POINTER(WsConfig)]),
     "ws_output_shape": (C.c_int, [C.POINTER(WsConfig), C.c_size_t, C.c_size_t,
                                   C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -102,6 +106,17 @@ SIGNATURES = {
     "ws_plan_strip_edges": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_size_t),
                                       C.POINTER(C.c_uint32)]),
     "ws_plan_union_edges": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint8]),
+    "ws_plan_strip_begin_async": (C.c_int, [_P, C.POINTER(WsConfig), C.POINTER(WsStrip), _P, _P, C.c_size_t]),
+    "ws_plan_strip_export_times_async": (C.c_int, [_P, _P, _P]),
+    "ws_plan_strip_import_times_async": (C.c_int, [_P, _P, _P, _P]),
+    "ws_plan_strip_labels_async": (C.c_int, [_P]),
+    "ws_plan_strip_export_labels_async": (C.c_int, [_P, _P, _P]),
+    "ws_plan_strip_import_labels_async": (C.c_int, [_P, _P, _P, _P]),
+    "ws_plan_strip_labels_finish_async": (C.c_int, [_P]),
+    "ws_plan_strip_check": (C.c_int, [_P]),
+    "ws_strip_packet_bytes": (C.c_size_t, [C.c_size_t]),
+    "ws_plan_strip_forest": (C.c_int, [_P, C.c_size_t, _P]),
+    "ws_plan_forest_packets": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_uint8]),
     "ws_plan_stats": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8)]),
     "ws_plan_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float * 4)]),
 }
@@ -148,8 +163,19 @@ def image_view(img: np.ndarray) -> WsImage:
     return WsImage(img.ctypes.data, img.shape[0], img.shape[1], img.strides[0], img.strides[1])
 
 
-def seeds_array(seeds) -> np.ndarray:
-    """&[(usize, usize)] -> C-contiguous [n][2] uint64."""
+class AutoSeeds:
+    """Stands for `seeds = find_local_minima(image)` computed on the device (WS_SEEDS_AUTO)."""
+    shape = (WS_SEEDS_AUTO, 2)
+
+    class _Null:
+        data = None
+    ctypes = _Null()
+
+
+def seeds_array(seeds):
+    """&[(usize, usize)] -> C-contiguous [n][2] uint64 (None: the engine finds the local maxima itself)."""
+    if seeds is None:
+        return AutoSeeds()
     a = np.asarray(seeds)
     if a.size == 0:
         return np.zeros((0, 2), dtype=np.uint64)
@@ -214,6 +240,13 @@ class Context:
 
     def synchronize(self):
         self.check(self.lib.ws_ctx_synchronize(self.handle))
+
+    def set_host_threads(self, n: int):
+        """Threads that stage pageable caller memory (0 = default)."""
+        self.check(self.lib.ws_ctx_set_host_threads(self.handle, int(n)))
+
+    def set_option(self, opt: int, value: int):
+        self.check(self.lib.ws_ctx_set_option(self.handle, int(opt), int(value)))
 
     def set_tie_seed(self, seed: int):
         """Key of the WS_TIE_RANDOM generator (default: drawn from the OS per context, like thread_rng)."""
@@ -314,6 +347,46 @@ class Plan:
     def union_edges(self, d_ab: int, d_w: int, n: int, ncolours: int, ndistinct: int, max_water_level: int):
         self.ctx.check(self.lib.ws_plan_union_edges(self.handle, d_ab or None, d_w or None, n, ncolours, ndistinct,
                                                     max_water_level))
+
+    # -- the same without host synchronisation (several exchange rounds in flight) ----------
+    def strip_begin_async(self, kind: int, max_water_level: int, global_rows: int, row_offset: int, halo_top: bool,
+                          halo_bottom: bool, colour_base: int, d_img: int, d_seeds_rc: int, nseeds: int):
+        cfg = make_config(kind, max_water_level, False)
+        st = WsStrip(global_rows, row_offset, 1 if halo_top else 0, 1 if halo_bottom else 0, colour_base)
+        self.ctx.check(self.lib.ws_plan_strip_begin_async(self.handle, C.byref(cfg), C.byref(st), d_img, d_seeds_rc,
+                                                          nseeds))
+
+    def strip_export_times_async(self, d_top: int, d_bottom: int):
+        self.ctx.check(self.lib.ws_plan_strip_export_times_async(self.handle, d_top or None, d_bottom or None))
+
+    def strip_import_times_async(self, d_top: int, d_bottom: int, d_changed: int):
+        self.ctx.check(self.lib.ws_plan_strip_import_times_async(self.handle, d_top or None, d_bottom or None, d_changed))
+
+    def strip_labels_async(self):
+        self.ctx.check(self.lib.ws_plan_strip_labels_async(self.handle))
+
+    def strip_export_labels_async(self, d_top: int, d_bottom: int):
+        self.ctx.check(self.lib.ws_plan_strip_export_labels_async(self.handle, d_top or None, d_bottom or None))
+
+    def strip_import_labels_async(self, d_top: int, d_bottom: int, d_pending: int):
+        self.ctx.check(self.lib.ws_plan_strip_import_labels_async(self.handle, d_top or None, d_bottom or None,
+                                                                  d_pending))
+
+    def strip_labels_finish_async(self):
+        self.ctx.check(self.lib.ws_plan_strip_labels_finish_async(self.handle))
+
+    def strip_check(self):
+        self.ctx.check(self.lib.ws_plan_strip_check(self.handle))
+
+    def strip_packet_bytes(self) -> int:
+        return int(self.lib.ws_strip_packet_bytes(self.cols))
+
+    def strip_forest(self, ncolours_total: int, d_packet: int):
+        self.ctx.check(self.lib.ws_plan_strip_forest(self.handle, ncolours_total, d_packet))
+
+    def forest_packets(self, d_packets: int, n_packets: int, ncolours_total: int, max_water_level: int):
+        self.ctx.check(self.lib.ws_plan_forest_packets(self.handle, d_packets, n_packets, ncolours_total,
+                                                       max_water_level))
 
     def snapshot(self, kind: int, i: int, level: int, d_out: int):
         self.ctx.check(self.lib.ws_plan_snapshot(self.handle, kind, i, level, d_out))

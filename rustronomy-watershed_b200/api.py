@@ -225,11 +225,16 @@ class Watershed(WatershedUtils, Generic[T]):
         hook = self.wlvl_hook
         results: list = []
         errors: list = []
-        seed_list = [(i + 1, (int(r), int(c))) for i, (r, c) in enumerate(s)]
+        seed_cache: list = []
 
         def _cb(_user, hp):
             h = hp.contents
             try:
+                if not seed_cache:      # (colour, (row, col)) as HookCtx carries them (lib.rs:849), from the C side
+                    tri = np.frombuffer((C.c_uint64 * (3 * h.nseeds)).from_address(h.seeds), dtype=np.uint64) \
+                        if h.nseeds else np.zeros(0, np.uint64)
+                    seed_cache.append([(int(a), (int(r), int(c))) for a, r, c in tri.reshape(-1, 3)])
+                seed_list = seed_cache[0]
                 n = h.rows * h.cols
                 image = np.frombuffer((C.c_uint8 * n).from_address(h.image), dtype=np.uint8).reshape(h.rows, h.cols)
                 colours = np.frombuffer((C.c_uint64 * n).from_address(h.colours), dtype=np.uint64).reshape(h.rows, h.cols)

@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libws_b200.so")
-SOURCES = ["kernels.cu", "flood.cu", "labels.cu", "merge.cu", "engine.cu"]
-HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "ws_b200.h")]
+SOURCES = ["kernels.cu", "flood.cu", "labels.cu", "merge.cu", "forest.cu", "engine.cu"]
+HEADERS = ["common.cuh", "kernels.cuh", "hostpipe.h", os.path.join("..", "..", "include", "ws_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -32,7 +33,7 @@ struct ws_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
-  int flood_grid = 0, jump_grid = 0, union_grid = 0;
+  int flood_grid = 0, jump_grid = 0, union_grid = 0, forest_grid = 0, sms = 0;
   std::string err;
   uint64_t tie_seed = 0;      // key of the WS_TIE_RANDOM generator
   ws_plan* cached = nullptr;  // workspace reused by the host-level entry points
@@ -52,6 +53,8 @@ struct ws_ctx {
   int host_threads_wanted = 0;     // 0: default (min(16, CPUs this process may use), WS_HOST_THREADS)
   bool pinned_host_widen = false;  // page-locked label outputs: u32 over the link + widening by the workers
   uint8_t* ring = nullptr;
+  bool ring_used[8] = {false, false, false, false, false, false, false, false};  // ring_ev[i] has been recorded
+  size_t ring_pos = 0;             // slots are handed out round robin ACROSS calls
   cudaEvent_t ring_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -60,6 +63,8 @@ struct ws_plan {
   ImageDims d{};
   FloodBuffers fb{};
   MergeBuffers mb{};
+  ForestBuffers fo{};
+  size_t fo_col_cap = 0, fo_edge_cap = 0, fo_def_cap = 0;
   size_t uf_cap = 0, edges_cap = 0, rep_cap = 0;
   uint32_t* rep = nullptr;
   int rep_level = -1;
@@ -226,7 +231,9 @@ extern "C" ws_status ws_ctx_create(int device, ws_ctx** out) {
   c->flood_grid = flood_max_grid(device);
   c->jump_grid = jump_max_grid(device);
   c->union_grid = union_max_grid(device);
-  if (c->flood_grid <= 0 || c->jump_grid <= 0 || c->union_grid <= 0) {
+  c->forest_grid = forest_max_grid(device);
+  cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
+  if (c->flood_grid <= 0 || c->jump_grid <= 0 || c->union_grid <= 0 || c->forest_grid <= 0) {
     cudaGetLastError();
     ws_ctx_destroy(c);
     return WS_ERR_CUDA;  // e.g. the fatbin holds no code for this GPU
@@ -336,9 +343,13 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->mb.fin_hist, n_img * 256 * 4);
   alloc((void**)&p->mb.ndistinct, n_img * 4);
   alloc((void**)&p->mb.counts, n_img * 256 * 4);
+  alloc((void**)&p->fo.count, 64);
+  alloc((void**)&p->fo.tile_hist, n_img * 256 * 4);
+  alloc((void**)&p->fo.forest_hist, n_img * 256 * 4);
   alloc((void**)&p->chunk_counts, minima_num_chunks(p->d) * 4);
   alloc((void**)&p->d_total, 16);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_ctrl, (FC_WORDS + 4) * 4);
+  if (e == cudaSuccess) e = cudaMemset(p->fo.count, 0, 64);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&p->h_ctrl, (FC_WORDS + 16) * 4);
   if (e == cudaSuccess) e = flood_make_tensor_maps(p->fb, p->d, p->tmaps);
   for (auto& ev : p->ev)
     if (e == cudaSuccess) e = cudaEventCreate(&ev);
@@ -380,6 +391,17 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->mb.fin_hist);
   cudaFree(p->mb.ndistinct);
   cudaFree(p->mb.counts);
+  cudaFree(p->fo.count);
+  cudaFree(p->fo.tile_hist);
+  cudaFree(p->fo.forest_hist);
+  cudaFree(p->fo.best);
+  cudaFree(p->fo.orig[0]);
+  cudaFree(p->fo.orig[1]);
+  cudaFree(p->fo.ab[1]);
+  cudaFree(p->fo.w[0]);
+  cudaFree(p->fo.w[1]);
+  cudaFree(p->fo.def_ab);
+  cudaFree(p->fo.def_w);
   cudaFree(p->rep);
   cudaFree(p->chunk_counts);
   cudaFree(p->d_total);
@@ -412,22 +434,25 @@ extern "C" ws_status ws_plan_find_local_minima(ws_plan* p, const uint8_t* d_imgs
   return WS_OK;
 }
 
-static ws_status plan_merge(ws_plan* p) {
+// union-find arrays of the level-ordered pass (merge tree) -- also lent to the forest rounds
+static ws_status plan_uf_buffers(ws_plan* p, size_t ncolours) {
   ws_ctx* ctx = p->ctx;
-  cudaStream_t s = ctx->stream;
-  const uint32_t lmax = p->cfg.max_water_level;
-  // union-find arrays sized to the seed list
-  if (p->nseeds > p->uf_cap || !p->mb.parent) {
+  if (ncolours > p->uf_cap || !p->mb.parent) {
     cudaFree(p->mb.parent); cudaFree(p->mb.hook_to); cudaFree(p->mb.hook_lvl);
     p->mb.parent = p->mb.hook_to = nullptr; p->mb.hook_lvl = nullptr; p->uf_cap = 0;
-    const size_t n = std::max<size_t>(p->nseeds, 1);
+    const size_t n = std::max<size_t>(ncolours, 1);
     WS_CUDA(ctx, cudaMalloc((void**)&p->mb.parent, n * 4));
     WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_to, n * 4));
     WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_lvl, n));
     p->uf_cap = n;
   }
-  // edge buffers: bounded by (nodes per tile - 1) forest edges per tile, so no host round trip is needed
-  const size_t cap = merge_reduce_capacity(p->d);
+  return WS_OK;
+}
+
+// edge buffers: bounded by (nodes per tile - 1) forest edges per tile, so no host round trip is needed
+static ws_status plan_edge_buffers(ws_plan* p, size_t min_cap = 0) {
+  ws_ctx* ctx = p->ctx;
+  const size_t cap = std::max(merge_reduce_capacity(p->d), min_cap);
   if (cap > p->edges_cap || !p->mb.edges) {
     cudaFree(p->mb.edges); cudaFree(p->mb.red_ab); cudaFree(p->mb.red_w);
     p->mb.edges = p->mb.red_ab = nullptr; p->mb.red_w = nullptr; p->edges_cap = 0;
@@ -436,7 +461,66 @@ static ws_status plan_merge(ws_plan* p) {
     WS_CUDA(ctx, cudaMalloc((void**)&p->mb.edges, cap * sizeof(uint2)));
     p->edges_cap = cap;
   }
-  // Lake counts: only the DEFERRED edges go through the global union-find; FINAL edges are counted.
+  return WS_OK;
+}
+
+// Buffers of the Boruvka rounds (forest.cu) for `ncolours` nodes and `def_cap` DEFERRED picks (0: one GPU, no
+// open nodes).  parent / link / open_ are the union-find arrays of the level-ordered pass (never in use at the
+// same time: that pass re-initialises them), ab[0] is its bucket array.
+static ws_status plan_forest_buffers(ws_plan* p, size_t ncolours, size_t def_cap, size_t min_edge_cap = 0) {
+  ws_ctx* ctx = p->ctx;
+  WS_TRY(plan_uf_buffers(p, ncolours));
+  WS_TRY(plan_edge_buffers(p, min_edge_cap));
+  if (ncolours > p->fo_col_cap || !p->fo.best) {
+    cudaFree(p->fo.best);
+    p->fo.best = nullptr; p->fo_col_cap = 0;
+    const size_t n = std::max<size_t>(ncolours, 1);
+    WS_CUDA(ctx, cudaMalloc((void**)&p->fo.best, n * 8));
+    p->fo_col_cap = n;
+  }
+  const size_t edge_cap = p->edges_cap;
+  if (edge_cap > p->fo_edge_cap || !p->fo.ab[1]) {
+    cudaFree(p->fo.ab[1]); cudaFree(p->fo.w[0]); cudaFree(p->fo.w[1]); cudaFree(p->fo.orig[0]); cudaFree(p->fo.orig[1]);
+    p->fo.ab[1] = p->fo.orig[0] = p->fo.orig[1] = nullptr; p->fo.w[0] = p->fo.w[1] = nullptr; p->fo_edge_cap = 0;
+    WS_CUDA(ctx, cudaMalloc((void**)&p->fo.ab[1], edge_cap * sizeof(uint2)));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->fo.w[0], edge_cap));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->fo.w[1], edge_cap));
+    p->fo_edge_cap = edge_cap;
+  }
+  if (def_cap && (!p->fo.orig[0] || def_cap > p->fo_def_cap)) {   // strips only
+    cudaFree(p->fo.def_ab); cudaFree(p->fo.def_w);
+    p->fo.def_ab = nullptr; p->fo.def_w = nullptr; p->fo_def_cap = 0;
+    if (!p->fo.orig[0]) {
+      WS_CUDA(ctx, cudaMalloc((void**)&p->fo.orig[0], edge_cap * sizeof(uint2)));
+      WS_CUDA(ctx, cudaMalloc((void**)&p->fo.orig[1], edge_cap * sizeof(uint2)));
+    }
+    WS_CUDA(ctx, cudaMalloc((void**)&p->fo.def_ab, def_cap * sizeof(uint2)));
+    WS_CUDA(ctx, cudaMalloc((void**)&p->fo.def_w, def_cap));
+    p->fo_def_cap = def_cap;
+  }
+  p->fo.def_cap = (uint32_t)p->fo_def_cap;
+  p->fo.parent = p->mb.parent;
+  p->fo.link = p->mb.hook_to;
+  p->fo.open_ = p->mb.hook_lvl;
+  p->fo.ab[0] = p->mb.edges;
+  p->fo.n_deferred = p->fo.count + 2;
+  p->fo.rounds = p->fo.count + 3;
+  p->fo.error = p->fo.count + 4;
+  return WS_OK;
+}
+
+static bool merge_by_kruskal() {  // A/B switch of the first version (level-ordered union-find, 255 grid barriers)
+  static const bool v = [] { const char* e = getenv("WS_MERGE_KRUSKAL"); return e && atoi(e) != 0; }();
+  return v;
+}
+
+static ws_status plan_merge(ws_plan* p) {
+  ws_ctx* ctx = p->ctx;
+  cudaStream_t s = ctx->stream;
+  const uint32_t lmax = p->cfg.max_water_level;
+  WS_TRY(plan_uf_buffers(p, p->nseeds));
+  WS_TRY(plan_edge_buffers(p));
+  // Per tile: FINAL forest edges (only counted) and DEFERRED edges between basins that reach the tile's rim.
   WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->seed_off, 1, p->mb.red_ab, p->mb.red_w,
                                    p->mb.red_count, s));
 #ifdef WS_MERGE_STATS
@@ -449,13 +533,24 @@ static ws_status plan_merge(ws_plan* p) {
             st[9] / (double)st[8], st[10] / (double)st[8]);
   }
 #endif
-  WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, 0, p->seed_off, p->d.n_img,
-                               p->mb.level_hist, p->mb.level_cursor, p->mb.fin_hist, p->mb.edges, s));
-  WS_CUDA(ctx, launch_uf_init(p->mb, p->d, (uint32_t)p->nseeds, s));
-  WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
-  WS_CUDA(ctx, launch_lake_counts(p->mb, p->d.n_img, lmax, s));
+  if (merge_by_kruskal()) {
+    WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, 0, p->seed_off, p->d.n_img,
+                                 p->mb.level_hist, p->mb.level_cursor, p->mb.fin_hist, p->mb.edges, s));
+    WS_CUDA(ctx, launch_uf_init(p->mb, p->d, (uint32_t)p->nseeds, s));
+    WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
+    WS_CUDA(ctx, launch_lake_counts(p->mb, p->d.n_img, lmax, s));
+    p->stats[4] += 8;
+  } else {
+    // The forest of the DEFERRED graph by Boruvka rounds: every node is closed here (the list is the whole
+    // graph), so every pick is a forest edge with its true level -- no order, no barrier per level.
+    WS_TRY(plan_forest_buffers(p, p->nseeds, 0));
+    WS_CUDA(ctx, launch_forest_init(p->fo, (uint32_t)p->nseeds, p->d.n_img, 0, ctx->sms, s));
+    WS_CUDA(ctx, launch_forest(p->fo, p->mb.red_ab, p->mb.red_w, p->mb.red_count, 1, 0, p->seed_off, p->d.n_img,
+                               ctx->forest_grid, ctx->sms, s));
+    WS_CUDA(ctx, launch_forest_lake_counts(p->mb.ndistinct, p->fo, p->d.n_img, lmax, p->mb.counts, s));
+    p->stats[4] += 5;
+  }
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
-  p->stats[4] += 8;
   p->merged = true;
   p->tree_built = false;
   p->rep_level = -1;
@@ -509,12 +604,13 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
   WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, cfg->tie_break == WS_TIE_RANDOM, ctx->tie_seed, s));
-  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
+  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, 1, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[3], s));
   p->stats[4] += 4 + (nseeds_total ? 1 : 0);
   if (cfg->kind == WS_MERGING) WS_TRY(plan_merge(p));
   WS_CUDA(ctx, cudaEventRecord(p->ev[4], s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl, p->fb.ctrl, FC_WORDS * 4, cudaMemcpyDeviceToHost, s));
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 10, p->fo.count + 3, 8, cudaMemcpyDeviceToHost, s));  // rounds, error
   p->h_seed_off.resize((size_t)p->d.n_img + 1);  // colour base of every slice, for merging snapshots
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_seed_off.data(), d_seed_off, ((size_t)p->d.n_img + 1) * 4,
                                cudaMemcpyDeviceToHost, s));
@@ -538,6 +634,8 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   }
   if (err & 16u) return fail(ctx, WS_ERR_INTERNAL, "flood worklist watchdog fired");
   if (err & 32u) return fail(ctx, WS_ERR_INTERNAL, "flood worklist: a ring slot was overwritten while in use");
+  if (p->merged && !merge_by_kruskal() && p->h_ctrl[FC_WORDS + 11])
+    return fail(ctx, WS_ERR_INTERNAL, "forest rounds failed");
   p->ran = true;
   return WS_OK;
 }
@@ -639,7 +737,13 @@ namespace {
 ws_status check_flood_errors(ws_plan* p) {
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl, p->fb.ctrl, FC_WORDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 10, p->fo.count + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (p->h_ctrl[FC_WORDS + 10]) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "forest rounds failed (error bits 0x%x)", p->h_ctrl[FC_WORDS + 10]);
+    return fail(ctx, WS_ERR_INTERNAL, msg);
+  }
   p->stats[0] += p->h_ctrl[FC_STALE];
   p->stats[1] += p->h_ctrl[FC_ACTIVATIONS];
   const uint32_t err = p->h_ctrl[FC_ERROR];
@@ -660,8 +764,8 @@ int first_owned(const ws_plan* p) { return p->d.halo_top ? 1 : 0; }
 int last_owned(const ws_plan* p) { return p->d.rows - 1 - (p->d.halo_bottom ? 1 : 0); }
 }  // namespace
 
-extern "C" ws_status ws_plan_strip_begin(ws_plan* p, const ws_config* cfg, const ws_strip* st, const uint8_t* d_img,
-                                         const uint32_t* d_seeds_rc, size_t nseeds) {
+static ws_status strip_begin_impl(ws_plan* p, const ws_config* cfg, const ws_strip* st, const uint8_t* d_img,
+                                  const uint32_t* d_seeds_rc, size_t nseeds, bool sync) {
   if (!p || !st || !d_img || (nseeds && !d_seeds_rc)) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
   WS_TRY(check_cfg(ctx, cfg));
@@ -685,9 +789,10 @@ extern "C" ws_status ws_plan_strip_begin(ws_plan* p, const ws_config* cfg, const
   for (auto& v : p->stats) v = 0;
   p->h_seed_off.assign(2, 0);
   p->h_seed_off[1] = (uint32_t)nseeds;
-  p->h_ctrl[FC_WORDS + 2] = 0;
-  p->h_ctrl[FC_WORDS + 3] = (uint32_t)nseeds;
-  WS_CUDA(ctx, cudaMemcpyAsync(p->d_strip_off, p->h_ctrl + FC_WORDS + 2, 8, cudaMemcpyHostToDevice, s));
+  // (a slot of its own: the copy reads it when it executes, which may be after this call has returned)
+  p->h_ctrl[FC_WORDS + 8] = 0;
+  p->h_ctrl[FC_WORDS + 9] = (uint32_t)nseeds;
+  WS_CUDA(ctx, cudaMemcpyAsync(p->d_strip_off, p->h_ctrl + FC_WORDS + 8, 8, cudaMemcpyHostToDevice, s));
   // hop counters cross strip boundaries through the halo exchange: the WHOLE field decides
   p->check_ovf = (size_t)st->global_rows * (size_t)p->d.cols > (size_t)HOP_MASK ? 1 : 0;
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_img, cfg->max_water_level, s));
@@ -695,24 +800,45 @@ extern "C" ws_status ws_plan_strip_begin(ws_plan* p, const ws_config* cfg, const
   p->bucket_shift = flood_bucket_shift(nseeds, p->d);
   WS_CUDA(ctx, launch_flood(p->fb, p->d, p->check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   p->stats[4] += 3;
+  return sync ? check_flood_errors(p) : WS_OK;
+}
+
+extern "C" ws_status ws_plan_strip_begin(ws_plan* p, const ws_config* cfg, const ws_strip* st, const uint8_t* d_img,
+                                         const uint32_t* d_seeds_rc, size_t nseeds) {
+  return strip_begin_impl(p, cfg, st, d_img, d_seeds_rc, nseeds, true);
+}
+extern "C" ws_status ws_plan_strip_begin_async(ws_plan* p, const ws_config* cfg, const ws_strip* st,
+                                               const uint8_t* d_img, const uint32_t* d_seeds_rc, size_t nseeds) {
+  return strip_begin_impl(p, cfg, st, d_img, d_seeds_rc, nseeds, false);
+}
+
+extern "C" ws_status ws_plan_strip_check(ws_plan* p) {
+  if (!p) return WS_ERR_INVALID_ARG;
+  WS_CUDA(p->ctx, cudaSetDevice(p->ctx->device));
   return check_flood_errors(p);
 }
 
-extern "C" ws_status ws_plan_strip_export_times(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom) {
+static ws_status strip_export_times_impl(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom, bool sync) {
   if (!p) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   WS_CUDA(ctx, launch_strip_export_T(p->fb.T, p->d, d_top ? first_owned(p) : -1, d_bottom ? last_owned(p) : -1, d_top,
                                      d_bottom, ctx->stream));
-  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller hands the rows to another stream / NCCL
+  if (sync) WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the caller hands the rows to another stream / NCCL
   return WS_OK;
 }
+extern "C" ws_status ws_plan_strip_export_times(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom) {
+  return strip_export_times_impl(p, d_top, d_bottom, true);
+}
+extern "C" ws_status ws_plan_strip_export_times_async(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom) {
+  return strip_export_times_impl(p, d_top, d_bottom, false);
+}
 
-extern "C" ws_status ws_plan_strip_import_times(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom,
-                                            int* changed) {
-  if (!p || !changed) return WS_ERR_INVALID_ARG;
+static ws_status strip_import_times_impl(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom, int* changed,
+                                         uint32_t* d_changed) {
+  if (!p || (!changed && !d_changed)) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
-  *changed = 0;
+  if (changed) *changed = 0;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
   // the worklist is empty after a completed flood; reset the statistics, keep the error word
@@ -723,36 +849,59 @@ extern "C" ws_status ws_plan_strip_import_times(ws_plan* p, const uint32_t* d_to
     WS_CUDA(ctx, launch_strip_import_T(p->fb, p->d, p->d.rows - 1, p->d.rows - 2, d_bottom, p->bucket_shift, s));
   WS_CUDA(ctx, launch_flood(p->fb, p->d, p->check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));  // returns at once if nothing woke up
   p->stats[4] += 3;
+  if (d_changed) {  // asynchronous: the flag goes to the caller's device word, nothing waits
+    WS_CUDA(ctx, launch_ctrl_accumulate(p->fb.ctrl + FC_STRIP_CHANGED, d_changed, 1, s));
+    return WS_OK;
+  }
   WS_TRY(check_flood_errors(p));
   *changed = p->h_ctrl[FC_STRIP_CHANGED] ? 1 : 0;
   return WS_OK;
 }
+extern "C" ws_status ws_plan_strip_import_times(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom,
+                                                int* changed) {
+  if (!changed) return WS_ERR_INVALID_ARG;
+  return strip_import_times_impl(p, d_top, d_bottom, changed, nullptr);
+}
+extern "C" ws_status ws_plan_strip_import_times_async(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom,
+                                                      uint32_t* d_changed) {
+  if (!d_changed) return WS_ERR_INVALID_ARG;
+  return strip_import_times_impl(p, d_top, d_bottom, nullptr, d_changed);
+}
 
-extern "C" ws_status ws_plan_strip_labels(ws_plan* p) {
+static ws_status strip_labels_impl(ws_plan* p, bool sync) {
   if (!p) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, p->cfg.tie_break == WS_TIE_RANDOM, ctx->tie_seed, ctx->stream));
-  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, ctx->stream));
+  // asynchronous protocol: the label plane is finished once, after the last exchange round
+  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, sync ? 1 : 0, ctx->stream));
   p->stats[4] += 2;
-  WS_TRY(check_flood_errors(p));
+  if (sync) WS_TRY(check_flood_errors(p));
   p->ran = true;
   return WS_OK;
 }
+extern "C" ws_status ws_plan_strip_labels(ws_plan* p) { return strip_labels_impl(p, true); }
+extern "C" ws_status ws_plan_strip_labels_async(ws_plan* p) { return strip_labels_impl(p, false); }
 
-extern "C" ws_status ws_plan_strip_export_labels(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom) {
+static ws_status strip_export_labels_impl(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom, bool sync) {
   if (!p) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
-  WS_CUDA(ctx, launch_strip_export_lab(p->fb.lab, p->d, d_top ? first_owned(p) : -1, d_bottom ? last_owned(p) : -1,
-                                       d_top, d_bottom, ctx->stream));
-  WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  WS_CUDA(ctx, launch_strip_export_lab(p->fb.lab, p->fb.rim, p->d, d_top ? first_owned(p) : -1,
+                                       d_bottom ? last_owned(p) : -1, d_top, d_bottom, ctx->stream));
+  if (sync) WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return WS_OK;
 }
+extern "C" ws_status ws_plan_strip_export_labels(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom) {
+  return strip_export_labels_impl(p, d_top, d_bottom, true);
+}
+extern "C" ws_status ws_plan_strip_export_labels_async(ws_plan* p, uint32_t* d_top, uint32_t* d_bottom) {
+  return strip_export_labels_impl(p, d_top, d_bottom, false);
+}
 
-extern "C" ws_status ws_plan_strip_import_labels(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom,
-                                                 size_t* pending) {
-  if (!p || !pending) return WS_ERR_INVALID_ARG;
+static ws_status strip_import_labels_impl(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom, size_t* pending,
+                                          uint32_t* d_pending) {
+  if (!p || (!pending && !d_pending)) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
@@ -760,11 +909,98 @@ extern "C" ws_status ws_plan_strip_import_labels(ws_plan* p, const uint32_t* d_t
   if (d_bottom && p->d.halo_bottom) WS_CUDA(ctx, launch_strip_import_lab(p->fb, p->d, p->d.rows - 1, d_bottom, s));
   WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl + FC_JUMP_FLAG0, 0, sizeof(uint32_t) * 3, s));
   WS_CUDA(ctx, cudaMemsetAsync(p->fb.ctrl + FC_STRIP_PENDING, 0, sizeof(uint32_t), s));
-  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, s));
-  WS_CUDA(ctx, launch_strip_count_pending(p->fb.lab, p->d, first_owned(p), last_owned(p), p->fb.ctrl, s));
+  if (d_pending) {  // asynchronous: only the rim array (a tenth of the label plane) is touched per round
+    WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, 0, s));
+    WS_CUDA(ctx, launch_strip_count_pending_rim(p->fb.rim, rim_words(p->d), p->fb.ctrl, ctx->sms, s));
+  } else {
+    WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, 1, s));
+    WS_CUDA(ctx, launch_strip_count_pending(p->fb.lab, p->d, first_owned(p), last_owned(p), p->fb.ctrl, s));
+  }
   p->stats[4] += 4;
+  if (d_pending) {
+    WS_CUDA(ctx, launch_ctrl_accumulate(p->fb.ctrl + FC_STRIP_PENDING, d_pending, 0, s));
+    return WS_OK;
+  }
   WS_TRY(check_flood_errors(p));
   *pending = p->h_ctrl[FC_STRIP_PENDING];
+  return WS_OK;
+}
+extern "C" ws_status ws_plan_strip_import_labels(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom,
+                                                 size_t* pending) {
+  if (!pending) return WS_ERR_INVALID_ARG;
+  return strip_import_labels_impl(p, d_top, d_bottom, pending, nullptr);
+}
+extern "C" ws_status ws_plan_strip_import_labels_async(ws_plan* p, const uint32_t* d_top, const uint32_t* d_bottom,
+                                                       uint32_t* d_pending) {
+  if (!d_pending) return WS_ERR_INVALID_ARG;
+  return strip_import_labels_impl(p, d_top, d_bottom, nullptr, d_pending);
+}
+
+// after the last exchange round of the asynchronous protocol: every label word takes its rim entry
+extern "C" ws_status ws_plan_strip_labels_finish_async(ws_plan* p) {
+  if (!p) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  WS_CUDA(ctx, launch_label_finish(p->fb, p->d, ctx->sms, ctx->stream));
+  p->stats[4] += 1;
+  return WS_OK;
+}
+
+// ---- strips, merging: the strip's FINAL counts and its boundary picks as one device-resident packet ----------
+// packet = uint32 header[260] { edges, colours present, error bits, 0, FINAL edges per level [256] }
+//          + cap x (colour a - 1, colour b - 1) uint32 pairs + cap level bytes,   cap = 3 * cols + 64
+// (at most one DEFERRED pick per boundary basin, and those live in at most three rows)
+static size_t strip_packet_cap(size_t cols) { return (3 * cols + 64 + 15) & ~(size_t)15; }
+extern "C" size_t ws_strip_packet_bytes(size_t cols) { return 260 * 4 + strip_packet_cap(cols) * 9; }
+
+extern "C" ws_status ws_plan_strip_forest(ws_plan* p, size_t ncolours_total, void* d_packet) {
+  if (!p || !d_packet) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  if (!p->ran) return fail(ctx, WS_ERR_INVALID_ARG, "labels are not resolved yet");
+  if (ncolours_total >= 0x7fffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "colour count too large");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t cap = strip_packet_cap((size_t)p->d.cols);
+  WS_TRY(plan_forest_buffers(p, ncolours_total, cap));
+  // labels are GLOBAL colours here (colour_base + i + 1), so the colour id is label - 1: offsets {0, ...}
+  WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, 1, p->mb.red_ab, p->mb.red_w,
+                                   p->mb.red_count, s));
+  WS_CUDA(ctx, launch_count_present(p->fb.lab, p->d, p->seeds, (uint32_t)p->nseeds, p->colour_base, p->mb.ndistinct, s));
+  WS_CUDA(ctx, launch_forest_init(p->fo, (uint32_t)ncolours_total, 1, 1, ctx->sms, s));
+  // open = the basins other strips may hold edges of: those on the halo rows, and on the first owned row below a
+  // halo (its upward edges belong to the strip above) -- the rows merge_reduce treats as rim
+  const size_t cols = (size_t)p->d.cols;
+  if (p->d.halo_top)
+    WS_CUDA(ctx, launch_forest_mark_open(p->fb.lab, 2 * cols, (uint32_t)ncolours_total, p->fo.open_, s));
+  if (p->d.halo_bottom)
+    WS_CUDA(ctx, launch_forest_mark_open(p->fb.lab + (size_t)(p->d.rows - 1) * cols, cols, (uint32_t)ncolours_total,
+                                         p->fo.open_, s));
+  WS_CUDA(ctx, launch_forest(p->fo, p->mb.red_ab, p->mb.red_w, p->mb.red_count, 1, 1, p->d_strip_off, 1,
+                             ctx->forest_grid, ctx->sms, s));
+  WS_CUDA(ctx, launch_strip_packet(p->fo, p->mb.ndistinct, (uint32_t)cap, d_packet, s));
+  p->stats[4] += 8;
+  p->merged = false;
+  return WS_OK;
+}
+
+// All strips' packets (gathered, back to back) -> lakes per level of the whole field in ws_plan_lake_counts().
+extern "C" ws_status ws_plan_forest_packets(ws_plan* p, const void* d_packets, size_t n_packets, size_t ncolours_total,
+                                            uint8_t max_water_level) {
+  if (!p || !d_packets || n_packets == 0) return WS_ERR_INVALID_ARG;
+  ws_ctx* ctx = p->ctx;
+  if (ncolours_total >= 0x7fffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "colour count too large");
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  const size_t cap = strip_packet_cap((size_t)p->d.cols);
+  WS_TRY(plan_forest_buffers(p, ncolours_total, cap, n_packets * cap));
+  WS_CUDA(ctx, launch_forest_init(p->fo, (uint32_t)ncolours_total, 1, 0, ctx->sms, s));
+  // edges -> ab[0] / w[0] (consumed by the first pass before the rounds reuse them), FINAL counts and colours summed
+  WS_CUDA(ctx, launch_strip_unpack(d_packets, (uint32_t)n_packets, (uint32_t)cap, p->fo, p->fo.count + 5,
+                                   p->mb.ndistinct, s));
+  WS_CUDA(ctx, launch_forest(p->fo, p->fo.ab[0], p->fo.w[0], p->fo.count + 5, 0, 0, p->d_strip_off, 1,
+                             ctx->forest_grid, ctx->sms, s));
+  WS_CUDA(ctx, launch_forest_lake_counts(p->mb.ndistinct, p->fo, 1, max_water_level, p->mb.counts, s));
+  p->stats[4] += 5;
   return WS_OK;
 }
 
@@ -775,15 +1011,7 @@ extern "C" ws_status ws_plan_strip_edges(ws_plan* p, const void** d_ab, const vo
   if (!p->ran) return fail(ctx, WS_ERR_INVALID_ARG, "labels are not resolved yet");
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  const size_t cap = merge_reduce_capacity(p->d);
-  if (cap > p->edges_cap || !p->mb.edges) {
-    cudaFree(p->mb.edges); cudaFree(p->mb.red_ab); cudaFree(p->mb.red_w);
-    p->mb.edges = p->mb.red_ab = nullptr; p->mb.red_w = nullptr; p->edges_cap = 0;
-    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.red_ab, cap * sizeof(uint2)));
-    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.red_w, cap));
-    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.edges, cap * sizeof(uint2)));
-    p->edges_cap = cap;
-  }
+  WS_TRY(plan_edge_buffers(p));
   // labels are GLOBAL colours here (colour_base + i + 1), so the colour id is label - 1: offsets {0, ...}
   WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, 1, p->mb.red_ab, p->mb.red_w,
                                    p->mb.red_count, s));
@@ -807,15 +1035,7 @@ extern "C" ws_status ws_plan_union_edges(ws_plan* p, const void* d_ab, const voi
   if (ncolours >= 0x7fffffffull || n >= 0xffffffffull) return fail(ctx, WS_ERR_TOO_LARGE, "edge or colour count too large");
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream;
-  if (ncolours > p->uf_cap || !p->mb.parent) {
-    cudaFree(p->mb.parent); cudaFree(p->mb.hook_to); cudaFree(p->mb.hook_lvl);
-    p->mb.parent = p->mb.hook_to = nullptr; p->mb.hook_lvl = nullptr; p->uf_cap = 0;
-    const size_t m = std::max<size_t>(ncolours, 1);
-    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.parent, m * 4));
-    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_to, m * 4));
-    WS_CUDA(ctx, cudaMalloc((void**)&p->mb.hook_lvl, m));
-    p->uf_cap = m;
-  }
+  WS_TRY(plan_uf_buffers(p, ncolours));
   if (n > p->union_edges_cap || !p->union_edges) {
     cudaFree(p->union_edges);
     p->union_edges = nullptr; p->union_edges_cap = 0;
@@ -864,6 +1084,26 @@ ws_status check_image(ws_ctx* ctx, const ws_image* img) {
   return WS_OK;
 }
 
+// WS_TRACE=1: wall time of the phases of a host-level call on stderr (synchronises between the phases)
+struct Trace {
+  bool on;
+  ws_ctx* ctx;
+  std::chrono::steady_clock::time_point t;
+  explicit Trace(ws_ctx* c) : ctx(c) {
+    static const bool env = [] { const char* e = getenv("WS_TRACE"); return e && atoi(e) != 0; }();
+    on = env;
+    if (on) t = std::chrono::steady_clock::now();
+  }
+  void lap(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ws trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 // ---- staged copies between pageable caller memory and the device (hostpipe.h) --------------------------
 constexpr size_t RING_SLOT_BYTES = (size_t)32 << 20;
 constexpr int RING_SLOTS = 4;
@@ -902,15 +1142,17 @@ ws_status staged_h2d(ws_ctx* ctx, void* d_dst, size_t total, Fill fill) {
   cudaStream_t s = ctx->stream;
   const size_t nchunks = (total + RING_SLOT_BYTES - 1) / RING_SLOT_BYTES;
   for (size_t k = 0; k < nchunks; ++k) {
-    const int slot = (int)(k % RING_SLOTS);
-    if (k >= (size_t)RING_SLOTS) WS_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
+    // the slot's last copy -- of this call or of an earlier one (the image, when the seeds follow) -- must
+    // have left it before the workers write into it again
+    const int slot = (int)(ctx->ring_pos++ % RING_SLOTS);
+    if (ctx->ring_used[slot]) WS_CUDA(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
     const size_t off = k * RING_SLOT_BYTES, n = std::min(RING_SLOT_BYTES, total - off);
     uint8_t* sp = ctx->ring + (size_t)slot * RING_SLOT_BYTES;
     pool_split(ctx, n, [&](size_t lo, size_t len) { fill(sp + lo, off + lo, len); });
     WS_CUDA(ctx, cudaMemcpyAsync((char*)d_dst + off, sp, n, cudaMemcpyHostToDevice, s));
     WS_CUDA(ctx, cudaEventRecord(ctx->ring_ev[slot], s));
+    ctx->ring_used[slot] = true;
   }
-  // the ring may be reused by the next staged copy: its slots are guarded by the same events
   return WS_OK;
 }
 
@@ -921,11 +1163,12 @@ ws_status staged_d2h(ws_ctx* ctx, const void* d_src, size_t total, Drain drain) 
   if (total == 0) return WS_OK;
   WS_TRY(ensure_ring(ctx));
   cudaStream_t s = ctx->stream;
-  // (slots still in flight from an earlier staged_h2d on this stream are ordered before these copies)
+  // (a slot still being read by an earlier staged_h2d is safe: these copies are behind it on the same stream)
   const size_t nchunks = (total + RING_SLOT_BYTES - 1) / RING_SLOT_BYTES;
   for (size_t k = 0; k < nchunks + RING_SLOTS - 1; ++k) {
     if (k < nchunks) {
       const int slot = (int)(k % RING_SLOTS);
+      ctx->ring_used[slot] = true;
       const size_t off = k * RING_SLOT_BYTES, n = std::min(RING_SLOT_BYTES, total - off);
       WS_CUDA(ctx, cudaMemcpyAsync(ctx->ring + (size_t)slot * RING_SLOT_BYTES, (const char*)d_src + off, n,
                                    cudaMemcpyDeviceToHost, s));
@@ -992,11 +1235,13 @@ ws_status upload_image(ws_ctx* ctx, const ws_image* img, uint8_t* dst) {
 // pageable way if the caller asked for it: WS_OPT_PINNED_HOST_WIDEN).
 ws_status download_labels_u64(ws_ctx* ctx, ws_plan* p, const uint32_t* d_lab, size_t n, uint64_t* out) {
   cudaStream_t s = ctx->stream;
+  Trace tr(ctx);
   if (!host_ptr_is_pinned(out) || ctx->pinned_host_widen) {
     WS_TRY(staged_d2h(ctx, d_lab, n * 4, [=](const uint8_t* sp, size_t off, size_t len) {
       widen_labels_host(out + off / 4, reinterpret_cast<const uint32_t*>(sp), len / 4);
     }));
     WS_CUDA(ctx, cudaStreamSynchronize(s));
+    tr.lap("labels: u32 down + host widen");
     return WS_OK;
   }
   const size_t chunk = (size_t)8 << 20;  // pixels per chunk: 64 MB of usize
@@ -1015,6 +1260,7 @@ ws_status download_labels_u64(ws_ctx* ctx, ws_plan* p, const uint32_t* d_lab, si
   }
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   WS_CUDA(ctx, cudaStreamSynchronize(s));
+  tr.lap("labels: device widen + u64 down");
   return WS_OK;
 }
 
@@ -1068,6 +1314,8 @@ ws_status host_run_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs,
     if (view) WS_TRY(upload_image(ctx, view, ctx->d_img));
     else WS_TRY(copy_h2d(ctx, ctx->d_img, imgs, n_img * npx_in));
   }
+  Trace tr(ctx);
+  tr.lap("image upload (+ earlier work)");
   WS_TRY(grow(ctx, ctx->d_seed_off, ctx->d_seed_off_cap, n_img + 1));
   if (auto_seeds) {
     // WatershedUtils::find_local_minima on the device: nothing but the image crosses the link
@@ -1102,7 +1350,9 @@ ws_status host_run_batch(ws_ctx* ctx, const ws_config* cfg, const uint8_t* imgs,
     }
     WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_seed_off, p->h_seed_off.data(), (n_img + 1) * 4, cudaMemcpyHostToDevice, s));
   }
+  tr.lap("seeds upload / search");
   WS_TRY(ws_plan_run(p, cfg, ctx->d_img, ctx->d_seeds, ctx->d_seed_off, nseeds));
+  tr.lap("device run");
   hr->plan = p;
   hr->orows = orows;
   hr->ocols = ocols;
@@ -1359,11 +1609,19 @@ extern "C" ws_status ws_transform_with_hook(ws_ctx* ctx, const ws_config* cfg, c
   std::vector<uint8_t> h_img(hr.npx);
   WS_CUDA(ctx, cudaMemcpyAsync(h_img.data(), ctx->d_img, hr.npx, cudaMemcpyDeviceToHost, ctx->stream));
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const bool auto_seeds = nseeds == WS_SEEDS_AUTO;
+  nseeds = hr.nseeds;
   std::vector<uint64_t> h_seeds(3 * std::max<size_t>(nseeds, 1));
+  std::vector<uint32_t> found;
+  if (auto_seeds && nseeds) {  // the list found on the device
+    found.resize(2 * nseeds);
+    WS_CUDA(ctx, cudaMemcpyAsync(found.data(), ctx->d_seeds, 2 * nseeds * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   for (size_t i = 0; i < nseeds; ++i) {
     h_seeds[3 * i] = i + 1;
-    h_seeds[3 * i + 1] = seeds_rc[2 * i];
-    h_seeds[3 * i + 2] = seeds_rc[2 * i + 1];
+    h_seeds[3 * i + 1] = auto_seeds ? found[2 * i] : seeds_rc[2 * i];
+    h_seeds[3 * i + 2] = auto_seeds ? found[2 * i + 1] : seeds_rc[2 * i + 1];
   }
   ws_hook_ctx hc;
   hc.max_water_level = cfg->max_water_level;
@@ -1464,6 +1722,7 @@ extern "C" ws_status ws_transform_to_list(ws_ctx* ctx, const ws_config* cfg, con
                                           uint64_t* out_sizes) {
   if (!ctx || !out_sizes) return WS_ERR_INVALID_ARG;
   WS_TRY(check_cfg(ctx, cfg));
+  if (nseeds == WS_SEEDS_AUTO) return fail(ctx, WS_ERR_INVALID_ARG, "lake sizes are indexed by the caller's seed list");
   WS_TRY(lake_sizes_guard(ctx, cfg, nseeds));  // before any work is done
   HostRun hr;
   WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));
@@ -1493,6 +1752,7 @@ extern "C" ws_status ws_transform_lake_sizes_compact(ws_ctx* ctx, const ws_confi
                                                      uint64_t* out_lake_counts, uint64_t* out_sizes) {
   if (!ctx || !out_sizes) return WS_ERR_INVALID_ARG;
   WS_TRY(check_cfg(ctx, cfg));
+  if (nseeds == WS_SEEDS_AUTO) return fail(ctx, WS_ERR_INVALID_ARG, "lake sizes are indexed by the caller's seed list");
   WS_TRY(lake_sizes_guard(ctx, cfg, nseeds));
   HostRun hr;
   WS_TRY(host_run(ctx, cfg, img, seeds_rc, nseeds, &hr));

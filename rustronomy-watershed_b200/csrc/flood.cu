@@ -846,13 +846,36 @@ __global__ void __launch_bounds__(256) strip_import_T_kernel(FloodBuffers b, Ima
   }
 }
 
-__global__ void __launch_bounds__(256) strip_export_lab_kernel(const uint32_t* __restrict__ lab, ImageDims d, int ra,
+__device__ __forceinline__ uint32_t lab_through_rim(const uint32_t* lab, const uint32_t* rim, size_t p) {
+  const uint32_t v = ld_cg(lab + p);
+  if (v & LAB_RESOLVED) return v;
+  const uint32_t t = ld_cg(rim + v);   // the label plane may be unfinished: what the reference points at decides
+  return (t & LAB_RESOLVED) ? t : v;
+}
+__global__ void __launch_bounds__(256) strip_export_lab_kernel(const uint32_t* __restrict__ lab,
+                                                               const uint32_t* __restrict__ rim, ImageDims d, int ra,
                                                                int rb, uint32_t* __restrict__ out_a,
                                                                uint32_t* __restrict__ out_b) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d.cols) return;
-  if (ra >= 0) out_a[c] = ld_cg(lab + (size_t)ra * d.cols + c);
-  if (rb >= 0) out_b[c] = ld_cg(lab + (size_t)rb * d.cols + c);
+  if (ra >= 0) out_a[c] = lab_through_rim(lab, rim, (size_t)ra * d.cols + c);
+  if (rb >= 0) out_b[c] = lab_through_rim(lab, rim, (size_t)rb * d.cols + c);
+}
+
+__global__ void __launch_bounds__(256) strip_count_pending_rim_kernel(const uint32_t* __restrict__ rim, size_t n,
+                                                                      uint32_t* __restrict__ ctrl) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  int cnt = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    cnt += !(ld_cg(rim + i) & LAB_RESOLVED);
+  cnt = __syncthreads_count(cnt);  // (the number of THREADS with pending entries is enough for a zero test)
+  if (threadIdx.x == 0 && cnt) atomicAdd(&ctrl[FC_STRIP_PENDING], (uint32_t)cnt);
+}
+cudaError_t launch_strip_count_pending_rim(const uint32_t* rim, size_t n, uint32_t* ctrl, int sms, cudaStream_t s) {
+  const size_t want = (n + 255) / 256;
+  const size_t cap = (size_t)sms * 4;
+  strip_count_pending_rim_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), 256, 0, s>>>(rim, n, ctrl);
+  return cudaGetLastError();
 }
 
 // resolved labels of the neighbour's boundary row replace the pending words of halo row `row`, in the
@@ -891,9 +914,9 @@ cudaError_t launch_strip_import_T(FloodBuffers b, ImageDims d, int row, int nb_r
   strip_import_T_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(b, d, row, nb_row, in, bucket_shift);
   return cudaGetLastError();
 }
-cudaError_t launch_strip_export_lab(const uint32_t* lab, ImageDims d, int ra, int rb, uint32_t* out_a,
-                                    uint32_t* out_b, cudaStream_t s) {
-  strip_export_lab_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(lab, d, ra, rb, out_a, out_b);
+cudaError_t launch_strip_export_lab(const uint32_t* lab, const uint32_t* rim, ImageDims d, int ra, int rb,
+                                    uint32_t* out_a, uint32_t* out_b, cudaStream_t s) {
+  strip_export_lab_kernel<<<(d.cols + 255) / 256, 256, 0, s>>>(lab, rim, d, ra, rb, out_a, out_b);
   return cudaGetLastError();
 }
 cudaError_t launch_strip_import_lab(FloodBuffers b, ImageDims d, int row, const uint32_t* in, cudaStream_t s) {

@@ -74,8 +74,11 @@ cudaError_t launch_strip_export_T(const uint32_t* T, ImageDims d, int ra, int rb
                                   cudaStream_t s);
 cudaError_t launch_strip_import_T(FloodBuffers b, ImageDims d, int row, int nb_row, const uint32_t* in,
                                   int bucket_shift, cudaStream_t s);
-cudaError_t launch_strip_export_lab(const uint32_t* lab, ImageDims d, int ra, int rb, uint32_t* out_a,
-                                    uint32_t* out_b, cudaStream_t s);
+// (a word that is still a reference is looked up in the rim array: the label plane may be unfinished)
+cudaError_t launch_strip_export_lab(const uint32_t* lab, const uint32_t* rim, ImageDims d, int ra, int rb,
+                                    uint32_t* out_a, uint32_t* out_b, cudaStream_t s);
+// unresolved entries of the rim array incl. the pending halo slots, added to ctrl[FC_STRIP_PENDING]
+cudaError_t launch_strip_count_pending_rim(const uint32_t* rim, size_t n, uint32_t* ctrl, int sms, cudaStream_t s);
 cudaError_t launch_strip_import_lab(FloodBuffers b, ImageDims d, int row, const uint32_t* in, cudaStream_t s);
 cudaError_t launch_strip_count_pending(const uint32_t* lab, ImageDims d, int r0, int r1, uint32_t* ctrl,
                                        cudaStream_t s);
@@ -96,7 +99,8 @@ size_t rim_words(const ImageDims& d);
 // tie_random: draw the parent uniformly among the earlier neighbours (lib.rs:250-253) instead of taking the first
 cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, bool tie_random, uint64_t tie_seed,
                           cudaStream_t s);
-cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s);
+cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, int finish, cudaStream_t s);
+cudaError_t launch_label_finish(FloodBuffers b, ImageDims d, int sms, cudaStream_t s);
 
 // --- merging (find_merge + make_colour_map + recolour, lib.rs:393-542, 590-592) ---
 struct MergeBuffers {
@@ -134,6 +138,44 @@ cudaError_t launch_lake_counts(MergeBuffers m, int n_img, uint32_t lmax, cudaStr
 // rep[g] = representative of colour g at `level` (start from rep if `incremental`)
 cudaError_t launch_rep_table(const uint32_t* hook_to, const uint8_t* hook_lvl, uint32_t nseeds, uint32_t level,
                              int incremental, uint32_t* rep, cudaStream_t s);
+
+// --- minimum spanning forest of the DEFERRED graph by Boruvka rounds (forest.cu) ---
+struct ForestBuffers {
+  uint32_t* parent;            // [ncolours] hook pointers (written in the hook phase only)
+  uint32_t* link;              // [ncolours] identity of a closed node that moved along a FINAL edge
+  unsigned long long* best;    // [ncolours] lightest offer: (255 - round) << 56 | level << 32 | position
+  uint8_t* open_;              // [ncolours] 1: the node has edges this list does not hold (strip boundary basins)
+  uint2* ab[2];                // live edges as the current roots of their ends, alternating by round
+  uint8_t* w[2];
+  uint2* orig[2];              // strips: the edges' own ends
+  uint32_t* count;             // [2] live edges in ab[0] / ab[1]
+  uint32_t* n_deferred;        // DEFERRED picks (strips only)
+  uint32_t* rounds;
+  uint32_t* error;             // bit 0: round limit, bit 1: DEFERRED list full, bit 2: identity chain too long
+  uint2* def_ab;               // [def_cap] DEFERRED picks, between identities after forest_ident
+  uint8_t* def_w;
+  uint32_t def_cap;
+  uint32_t* tile_hist;         // [n_img][256] FINAL edges of the tiles per level
+  uint32_t* forest_hist;       // [n_img][256] FINAL picks of the rounds per level
+};
+int forest_max_grid(int device);
+// with_open: the run marks open nodes (strips); else every node is closed
+cudaError_t launch_forest_init(ForestBuffers f, uint32_t ncolours, int n_img, int with_open, int sms, cudaStream_t s);
+// open_[colour - 1] = 1 for the colours of `count` label words
+cudaError_t launch_forest_mark_open(const uint32_t* lab, size_t count, uint32_t ncolours, uint8_t* open_,
+                                    cudaStream_t s);
+// in_*: the edge list to start from; skip_final: entries with bit 31 of .y are FINAL tile edges (counted only)
+cudaError_t launch_forest(ForestBuffers f, const uint2* in_ab, const uint8_t* in_w, const uint32_t* in_count,
+                          int skip_final, int with_open, const uint32_t* seed_off, int n_img, int grid, int sms,
+                          cudaStream_t s);
+// strips: *dst |= (*src != 0) (as_flag) or *dst += *src
+cudaError_t launch_ctrl_accumulate(const uint32_t* src, uint32_t* dst, int as_flag, cudaStream_t s);
+// strips: header + DEFERRED picks of a finished forest run -> one packet; packets -> one edge list + summed header
+cudaError_t launch_strip_packet(ForestBuffers f, const uint32_t* ndistinct, uint32_t cap, void* packet, cudaStream_t s);
+cudaError_t launch_strip_unpack(const void* packets, uint32_t n_packets, uint32_t cap, ForestBuffers f,
+                                uint32_t* out_count, uint32_t* ndistinct, cudaStream_t s);
+cudaError_t launch_forest_lake_counts(const uint32_t* ndistinct, ForestBuffers f, int n_img, uint32_t lmax,
+                                      uint32_t* counts, cudaStream_t s);
 
 // --- per-level outputs (hooks of transform_history / transform_to_list) -----
 // out[p] = lvl[p] <= level ? label : 0, label optionally mapped through rep[] (merging)

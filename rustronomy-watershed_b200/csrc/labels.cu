@@ -101,12 +101,14 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
       const uint32_t tv = t[0];
       const size_t p = base + (size_t)r * d.cols + c;
       b.lvl[p] = (tv >= T_INF) ? (uint8_t)255 : (uint8_t)(tv >> 24);
-      if (tv >= T_INF) {
+      if (d.is_halo_row(r)) {
+        // a neighbouring strip owns this pixel: its slot behind the rim entries holds its own index ("pending")
+        // until that strip's colour is imported; a pixel that is never coloured is resolved (UNCOLOURED) at once
+        const uint32_t slot = rim_total + (r == 0 ? 0u : (uint32_t)d.cols) + (uint32_t)c;
+        if (tv < T_INF) term = slot;
+        b.rim[slot] = term;
+      } else if (tv >= T_INF) {
         // never coloured
-      } else if (d.is_halo_row(r)) {
-        // a neighbouring strip owns this pixel: its slot behind the rim entries holds its own index
-        term = rim_total + (r == 0 ? 0u : (uint32_t)d.cols) + (uint32_t)c;
-        b.rim[term] = term;
       } else if (tv == 0u) {
         term = __ldcg(b.lab + p);  // seed: coloured by seed_init
         ++nseed_px;
@@ -201,6 +203,9 @@ cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, bool
                           cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(ndistinct, 0, sizeof(uint32_t) * (size_t)d.n_img, s);
   if (e != cudaSuccess) return e;
+  // the pending slots of halo rows this plan does not have read as resolved (bit 31 set) to whoever counts them
+  e = cudaMemsetAsync(b.rim + (size_t)d.tiles_total() * RIM_PER_TILE, 0x80, 2 * (size_t)d.cols * sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
   if (tie_random) label_tile_kernel<true><<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d, ndistinct, tie_seed);
   else label_tile_kernel<false><<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d, ndistinct, 0ull);
   return cudaGetLastError();
@@ -266,7 +271,18 @@ static int coop_max_grid_rim(int device) {
 }
 int jump_max_grid(int device) { return coop_max_grid_rim(device); }
 
-cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s) {
+cudaError_t launch_label_finish(FloodBuffers b, ImageDims d, int sms, cudaStream_t s) {
+  const size_t n = d.px_total();
+  const size_t w2 = (n / 4 + 255) / 256;
+  const size_t cap = (size_t)sms * 16;
+  const unsigned g2 = (unsigned)(w2 < cap ? (w2 ? w2 : 1) : cap);
+  label_finish_kernel<<<g2, 256, 0, s>>>(b.lab, n, b.rim);
+  return cudaGetLastError();
+}
+
+// finish = 0: only the rim array is resolved (strips between two exchange rounds: the label plane is finished
+// once, after the last round -- it is 10x the rim array)
+cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, int finish, cudaStream_t s) {
   uint32_t* rim = b.rim;
   uint32_t* ctrl = b.ctrl;
   size_t total = (size_t)d.tiles_total() * RIM_PER_TILE;  // the pending slots never move by themselves
@@ -274,7 +290,7 @@ cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, cudaStream_t s) {
   const int g = (size_t)grid > want ? (int)(want ? want : 1) : grid;
   void* args[] = {&rim, &total, &ctrl};
   cudaError_t e = cudaLaunchCooperativeKernel((const void*)rim_jump_kernel, dim3(g), dim3(256), args, 0, s);
-  if (e != cudaSuccess) return e;
+  if (e != cudaSuccess || !finish) return e;
   const size_t n = d.px_total();
   const size_t w2 = (n / 4 + 255) / 256;
   const unsigned g2 = (unsigned)(w2 < (size_t)148 * 16 ? (w2 ? w2 : 1) : (size_t)148 * 16);

@@ -15,6 +15,14 @@ strip's rows plus one halo row per neighbour):
 
 `solve()` is written against two small interfaces so the same driver runs (a) one strip per rank under
 torch.distributed (NCCL on GPUs, gloo in the CPU tests), and (b) several strips in one process.
+
+On the GPU the protocol runs WITHOUT a host round trip per exchange round (`solve_async`): everything -- the
+library's kernels, the row copies, NCCL -- is enqueued on the library's stream, the "did anything change" /
+"is anything pending" answers accumulate in device words, and the host looks at them once per batch of rounds
+(rounds after the fixed point change nothing and cost a few tens of microseconds).  Step 4 exchanges no edge
+lists: every strip reduces its basin graph to the number of certain forest edges per level plus the few forest
+edges between basins on its boundary rows (csrc/forest.cu), and one all-gather of those packets (a few
+hundred KB per strip) feeds a last round of the same reduction on every rank.
 """
 from __future__ import annotations
 
@@ -95,6 +103,22 @@ class LocalComm:
     def allgather_edges(self, ab: List[torch.Tensor], w: List[torch.Tensor]):
         return torch.cat(ab) if ab else None, torch.cat(w) if w else None
 
+    # -- asynchronous protocol: nothing below waits for the device -------------------------------------
+    def exchange_rows(self, strips: Dict[int, "CudaStrip"], kind: str):
+        """send_{top,bottom} of every strip -> recv_{bottom,top} of its neighbour (device copies, stream ordered)."""
+        for sid, s in strips.items():
+            snd = s.rows_buf[kind]
+            if sid > 0:
+                strips[sid - 1].rows_buf[kind]["recv_bottom"].copy_(snd["send_top"], non_blocking=True)
+            if sid < self.n_strips - 1:
+                strips[sid + 1].rows_buf[kind]["recv_top"].copy_(snd["send_bottom"], non_blocking=True)
+
+    def reduce_flag(self, t: torch.Tensor, op: str) -> int:
+        return int(t.item())                      # the only wait of a batch of rounds
+
+    def allgather_packets(self, packets: List[torch.Tensor]) -> torch.Tensor:
+        return torch.cat(packets)
+
 
 class DistComm:
     """One strip per rank of a torch.distributed process group (NCCL on GPUs, gloo on CPU)."""
@@ -150,6 +174,30 @@ class DistComm:
         self.dist.all_gather(out, t, group=self.group)
         return [int(v.item()) for v in out]
 
+    # -- asynchronous protocol ---------------------------------------------------------------------------
+    def exchange_rows(self, strips, kind: str):
+        dist, r, n = self.dist, self.rank, self.n_strips
+        b = strips[r].rows_buf[kind]
+        ops = []
+        if r > 0:
+            ops.append(dist.P2POp(dist.isend, b["send_top"], r - 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, b["recv_top"], r - 1, self.group))
+        if r < n - 1:
+            ops.append(dist.P2POp(dist.isend, b["send_bottom"], r + 1, self.group))
+            ops.append(dist.P2POp(dist.irecv, b["recv_bottom"], r + 1, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()                        # orders the current stream behind the transfer; the host goes on
+
+    def reduce_flag(self, t: torch.Tensor, op: str) -> int:
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
+    def allgather_packets(self, packets):
+        out = torch.empty(self.n_strips * packets[0].numel(), dtype=torch.uint8, device=packets[0].device)
+        self.dist.all_gather_into_tensor(out, packets[0], group=self.group)
+        return out
+
     def allgather_edges(self, ab, w):
         """Variable-length all-gather: sizes first, then padded buffers."""
         a, b = ab[0], w[0]
@@ -188,8 +236,51 @@ class CudaStrip:
             self.plan.find_local_minima(self.img.data_ptr(), self.seeds.data_ptr(), self.nseeds, self.off.data_ptr())
         self.colour_base = 0
 
+        # the asynchronous protocol: everything runs on the library's stream, row buffers are reused
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=self.dev)
+        with torch.cuda.stream(self.stream):
+            self.rows_buf = {k: {n: torch.empty(self.cols, dtype=torch.int32, device=self.dev)
+                                 for n in ("send_top", "send_bottom", "recv_top", "recv_bottom")}
+                             for k in ("times", "labels")}
+            self.packet = torch.empty(self.plan.strip_packet_bytes(), dtype=torch.uint8, device=self.dev)
+
     def _row(self):
         return torch.empty(self.cols, dtype=torch.int32, device=self.dev)
+
+    def _ptr(self, kind: str, name: str, present: bool) -> int:
+        return self.rows_buf[kind][name].data_ptr() if present else 0
+
+    def begin_async(self, kind: int, lmax: int, colour_base: int):
+        g = self.geom
+        self.colour_base = colour_base
+        self.plan.strip_begin_async(kind, lmax, g.global_rows, g.local_rows[0], g.halo_top, g.halo_bottom, colour_base,
+                                    self.img.data_ptr(), self.seeds.data_ptr(), self.nseeds)
+
+    def export_async(self, kind: str):
+        g = self.geom
+        fn = self.plan.strip_export_times_async if kind == "times" else self.plan.strip_export_labels_async
+        fn(self._ptr(kind, "send_top", g.halo_top), self._ptr(kind, "send_bottom", g.halo_bottom))
+
+    def import_async(self, kind: str, acc: torch.Tensor):
+        g = self.geom
+        fn = self.plan.strip_import_times_async if kind == "times" else self.plan.strip_import_labels_async
+        fn(self._ptr(kind, "recv_top", g.halo_top), self._ptr(kind, "recv_bottom", g.halo_bottom), acc.data_ptr())
+
+    def labels_async(self):
+        self.plan.strip_labels_async()
+
+    def forest_async(self, ncolours_total: int) -> torch.Tensor:
+        self.plan.strip_forest(ncolours_total, self.packet.data_ptr())
+        return self.packet
+
+    def lakes_from_packets(self, packets: torch.Tensor, n_packets: int, ncolours_total: int, lmax: int) -> np.ndarray:
+        self.plan.forest_packets(packets.data_ptr(), n_packets, ncolours_total, lmax)
+        counts = self.ctx.d2h(self.plan.lake_counts_ptr, (256,), np.uint32)      # (waits for the stream)
+        self.plan.strip_check()
+        return counts
+
+    def check(self):
+        self.plan.strip_check()
 
     def begin(self, kind: int, lmax: int, colour_base: int):
         g = self.geom
@@ -271,8 +362,90 @@ class StripResult:
     phase_s: Optional[dict] = None        # wall seconds per phase of the protocol (this process)
 
 
+def solve_async(strips: Sequence, comm, kind: int = MERGING, max_water_level: int = 254, max_rounds: int = 100000,
+                first_batch: int = 4, batch: int = 2) -> StripResult:
+    """The protocol on GPUs with the exchange rounds kept in flight: the host waits once per batch of rounds."""
+    import time
+    by_id = {s.geom.sid: s for s in strips}
+    assert sorted(by_id) == sorted(comm.local_ids)
+    any_strip = next(iter(by_id.values()))
+    phase_s, t_last = {}, time.perf_counter()
+
+    def lap(name):
+        nonlocal t_last
+        now = time.perf_counter()
+        phase_s[name] = phase_s.get(name, 0.0) + now - t_last
+        t_last = now
+
+    counts = comm.allgather_ints({sid: s.nseeds for sid, s in by_id.items()})
+    bases = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    ncolours = int(bases[-1])
+    lap("seed counts (all-gather)")
+    with torch.cuda.stream(any_strip.stream):
+        acc = torch.zeros(1, dtype=torch.int32, device=any_strip.dev)
+        for sid, s in by_id.items():
+            s.begin_async(kind, max_water_level, int(bases[sid]))
+
+        def rounds_until(kind_name: str, op: str) -> int:
+            """Exchange rounds in batches; stops when the LAST round of a batch left `acc` at zero everywhere."""
+            done, size = 0, first_batch
+            while True:
+                for r in range(size):
+                    if r == size - 1:
+                        acc.zero_()                      # only the batch's last round decides
+                    for s in by_id.values():
+                        s.export_async(kind_name)
+                    comm.exchange_rows(by_id, kind_name)
+                    for s in by_id.values():
+                        s.import_async(kind_name, acc)
+                done += size
+                if comm.reduce_flag(acc, op) == 0:
+                    return done
+                if done >= max_rounds:
+                    raise RuntimeError("strip exchange did not converge")
+                size = batch
+
+        flood_rounds = rounds_until("times", "max")
+        lap("arrival-time exchange rounds")
+        for s in by_id.values():
+            s.labels_async()
+        label_rounds = rounds_until("labels", "sum")
+        # Every OWNED pixel is resolved now, but a halo row still shows what its owner exported at the start of
+        # the last round; the edges towards the halo rows need the final words: one more exchange.
+        for s in by_id.values():
+            s.export_async("labels")
+        comm.exchange_rows(by_id, "labels")
+        for s in by_id.values():
+            s.import_async("labels", acc)
+        label_rounds += 1
+        for s in by_id.values():
+            s.plan.strip_labels_finish_async()       # the label plane itself, once
+        lap("labels + label exchange rounds")
+
+        lake_counts, edges_total = None, 0
+        if kind == MERGING:
+            packets = [by_id[sid].forest_async(ncolours) for sid in sorted(by_id)]
+            gathered = comm.allgather_packets(packets)
+            first = by_id[sorted(by_id)[0]]
+            counts256 = first.lakes_from_packets(gathered, comm.n_strips, ncolours, max_water_level)
+            lake_counts = counts256[: max_water_level + 1].astype(np.uint64)
+            hdr = gathered.view(torch.int32)[: 4].cpu().numpy() if comm.n_strips == 1 else None
+            edges_total = int(hdr[0]) if hdr is not None else 0
+            lap("strip forests, packet all-gather, boundary forest")
+        for s in by_id.values():
+            s.check()
+    return StripResult(lake_counts, flood_rounds, label_rounds, ncolours, edges_total, phase_s)
+
+
 def solve(strips: Sequence, comm, kind: int = MERGING, max_water_level: int = 254, max_rounds: int = 100000) -> StripResult:
     """Run the protocol over the strips this process holds (`strips[i]` has geometry sid = comm.local_ids[i])."""
+    if strips and all(hasattr(s, "begin_async") for s in strips) and hasattr(comm, "exchange_rows"):
+        return solve_async(strips, comm, kind, max_water_level, max_rounds)
+    return solve_sync(strips, comm, kind, max_water_level, max_rounds)
+
+
+def solve_sync(strips: Sequence, comm, kind: int = MERGING, max_water_level: int = 254, max_rounds: int = 100000) -> StripResult:
+    """The protocol with a host decision after every exchange round (the CPU test backend; the first GPU version)."""
     import time
     by_id = {s.geom.sid: s for s in strips}
     assert sorted(by_id) == sorted(comm.local_ids)

@@ -155,6 +155,69 @@ def lake_counts(lab: np.ndarray, lvl: np.ndarray, nseeds: int, lmax: int = 254, 
     return ndistinct - np.cumsum(fin_hist + unions)[: lmax + 1]
 
 
+def forest_rounds(edges: np.ndarray, n_nodes: int, open_: np.ndarray = None):
+    """csrc/forest.cu: Boruvka rounds over an arbitrary edge list [n][3] = (a, b, level) with the same rules as the
+    tile kernel.  Returns (FINAL picks [k][3], DEFERRED picks between identities [m][3], rounds)."""
+    open_ = np.zeros(n_nodes, bool) if open_ is None else open_.copy()
+    parent = np.arange(n_nodes)
+    link = np.arange(n_nodes)
+    orig = edges[:, :2].copy()
+    cur = edges[:, :2].copy()          # current roots of the ends
+    w = edges[:, 2].copy()
+    F, D, rounds = [], [], 0
+    alive = cur[:, 0] != cur[:, 1]
+    orig, cur, w = orig[alive], cur[alive], w[alive]
+    while len(cur):
+        rounds += 1
+        key = w * (1 << 32) + np.arange(len(cur))
+        best = np.full(n_nodes, NONE)
+        np.minimum.at(best, cur[:, 0], key)
+        np.minimum.at(best, cur[:, 1], key)
+        new_parent = parent.copy()
+        for i in range(len(cur)):
+            ca, cb = cur[i]
+            pa, pb = best[ca] == key[i], best[cb] == key[i]
+            if not (pa or pb):
+                continue
+            cla, clb = not open_[ca], not open_[cb]
+            if pa and pb:
+                a_moves = (ca > cb) if cla == clb else cla
+            else:
+                a_moves = pa
+            mover, other = (ca, cb) if a_moves else (cb, ca)
+            mover_closed = cla if a_moves else clb
+            fin = mover_closed or (pa and pb and (cla or clb))
+            new_parent[mover] = other
+            if fin:
+                if mover_closed:
+                    link[mover] = orig[i][1] if a_moves else orig[i][0]
+                F.append((orig[i][0], orig[i][1], w[i]))
+            else:
+                D.append((orig[i][0], orig[i][1], w[i]))
+        parent = new_parent
+        roots = _find_roots(parent)
+        np.logical_or.at(open_, roots, open_.copy())
+        parent = roots.copy()
+        cur = roots[cur]
+        alive = cur[:, 0] != cur[:, 1]
+        orig, cur, w = orig[alive], cur[alive], w[alive]
+    ident = _find_roots(link)
+    D = np.array(D, np.int64).reshape(-1, 3)
+    if len(D):
+        D[:, 0], D[:, 1] = ident[D[:, 0]], ident[D[:, 1]]
+    return np.array(F, np.int64).reshape(-1, 3), D, rounds
+
+
+def lake_counts_forest(lab: np.ndarray, lvl: np.ndarray, nseeds: int, lmax: int = 254) -> np.ndarray:
+    """Lakes per level with the forest rounds instead of the level-ordered union (what the engine runs)."""
+    F, D, _ = reduce_image(lab, lvl, True)
+    ndistinct = len(np.unique(lab[lab != 0]))
+    F2, D2, rounds = forest_rounds(D, nseeds + 1)
+    assert len(D2) == 0, "every node is closed: no DEFERRED pick"
+    hist = np.bincount(np.concatenate([F[:, 2], F2[:, 2]]).astype(np.int64), minlength=256)
+    return ndistinct - np.cumsum(hist)[: lmax + 1]
+
+
 def partitions(lab: np.ndarray, lvl: np.ndarray, nseeds: int, levels, contract: bool = True):
     """Merging label images at `levels` from the merge tree built of ALL emitted edges (FINAL ones between the
     basins themselves, DEFERRED ones between identities), representative = smallest colour."""

@@ -37,6 +37,7 @@ def test_model_lake_counts_and_partitions(oracle, name):
     lab, lvl = seg.final.astype(np.int64), seg.lvl.astype(np.int64)
     got = mm.lake_counts(lab, lvl, len(seeds))
     assert np.array_equal(got, np.array(exp)), "lakes per level"
+    assert np.array_equal(mm.lake_counts_forest(lab, lvl, len(seeds)), np.array(exp)), "lakes per level (forest rounds)"
     parts = mm.partitions(lab, lvl, len(seeds), levels)
     for L in levels:
         assert oracle.same_partition(parts[L], snaps[L]), f"partition at level {L}"
@@ -44,3 +45,35 @@ def test_model_lake_counts_and_partitions(oracle, name):
     assert np.array_equal(mm.lake_counts(lab, lvl, len(seeds), contract=False), np.array(exp))
     F, D, rounds = mm.reduce_image(lab, lvl, contract=False)
     assert len(F) == 0
+
+
+def test_forest_rounds_with_open_nodes_compose(oracle):
+    """Strip-style use of the rounds: cut the DEFERRED graph of an image into two halves by node id, mark the
+    nodes that have edges in both halves open, run the rounds on each half, then on the union of the two
+    DEFERRED lists: FINAL counts per level must add up to the forest of the whole graph."""
+    img = fieldgen.uniform(128, 256, 11)
+    seeds = oracle.find_local_minima(img)
+    seg = oracle.transform(oracle.SEGMENTING, img, seeds)
+    lab, lvl = seg.final.astype(np.int64), seg.lvl.astype(np.int64)
+    _, D, _ = mm.reduce_image(lab, lvl, True)
+    n = len(seeds) + 1
+    whole, rest, _ = mm.forest_rounds(D, n)
+    assert len(rest) == 0
+    rng = np.random.default_rng(3)
+    side = rng.integers(0, 2, len(D)).astype(bool)          # which half owns an edge
+    touch = np.zeros((2, n), bool)
+    for h in (0, 1):
+        e = D[side == bool(h)]
+        touch[h, e[:, 0]] = True
+        touch[h, e[:, 1]] = True
+    open_ = touch[0] & touch[1]
+    hist = np.zeros(256, np.int64)
+    gathered = []
+    for h in (0, 1):
+        F, Dh, _ = mm.forest_rounds(D[side == bool(h)], n, open_)
+        hist += np.bincount(F[:, 2], minlength=256)
+        gathered.append(Dh)
+    F, Dg, _ = mm.forest_rounds(np.concatenate(gathered), n)
+    assert len(Dg) == 0
+    hist += np.bincount(F[:, 2], minlength=256)
+    assert np.array_equal(hist, np.bincount(whole[:, 2], minlength=256))
