@@ -254,12 +254,18 @@ def main():
     ctx.synchronize()
     seed_ms = 1e3 * (time.perf_counter() - t0)
 
+    kernel_ms = {}
+
     def step():
         plan.run(0, 254, d_img.data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), nseeds)   # segmenting
         a = plan.phase_ms()
+        ka = plan.kernel_ms()
         la = plan.stats()["kernel_launches"]
         plan.run(1, 254, d_img.data_ptr(), d_seeds.data_ptr(), d_off.data_ptr(), nseeds)   # merging
         b = plan.phase_ms()
+        kb = plan.kernel_ms()
+        for k in ka:                                   # CUDA events around every kernel, on the library's stream
+            kernel_ms.setdefault(k, []).append((ka[k], kb[k]))
         return [a["flood"], b["flood"]], la + plan.stats()["kernel_launches"], (a, b)
 
     def barrier():
@@ -290,6 +296,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     flood_ms, launches, phases = [], 0, None
+    kernel_ms.clear()
     for _ in range(args.steps):
         f, l, phases = step()
         flood_ms += f
@@ -489,17 +496,41 @@ def main():
     alg_bytes = npx * LEVELS * ALG_BYTES_PER_PX_LEVEL
     achieved = alg_bytes / (flood_avg_ms * 1e-3) / 1e9
     traffic = None
+    one_pass = npx * 5                                  # what ONE ideal pass would move: 1 B image in, 4 B arrival time out
+    # every kernel that takes >= 5 % of the step: live CUDA-event time, DRAM bytes per launch from the ncu capture
+    # named in profiles/kernel_traffic.json (file names carry the commit they were taken at)
+    ktraffic = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "flood_traffic.json"))).get(f"{args.field}_{S}")
+        ktraffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
     except Exception:
         pass
-    one_pass = npx * 5                                  # what ONE ideal pass would move: 1 B image in, 4 B arrival time out
-    roofline = {"kernel": "flood_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    kt = ktraffic.get(f"{args.field}_{S}", {})
+    kernels = []
+    step_ms = dev_ms / args.steps
+    for name, pairs in kernel_ms.items():
+        seg_ms = float(np.mean([p[0] for p in pairs]))
+        mrg_ms = float(np.mean([p[1] for p in pairs]))
+        launches_k = int(seg_ms > 0) + int(mrg_ms > 0)
+        if (seg_ms + mrg_ms) < 0.05 * step_ms or launches_k == 0:
+            continue
+        info = kt.get(name, {})
+        per_launch_ms = (seg_ms + mrg_ms) / launches_k
+        b = info.get("dram_bytes")
+        kernels.append({"name": name, "ms_per_step": seg_ms + mrg_ms, "launches_per_step": launches_k,
+                        "ms_per_launch": per_launch_ms, "share_of_step": (seg_ms + mrg_ms) / step_ms,
+                        "dram_bytes_per_launch": b,
+                        "frac_of_hbm_peak": (b / (per_launch_ms * 1e-3) / 1e9 / peak) if b else None,
+                        "ncu_capture": info.get("file")})
+    kernels.sort(key=lambda k: -k["ms_per_step"])
+    if traffic is None and "flood" in kt:
+        traffic = kt["flood"].get("dram_bytes")
+    roofline = {"dram_frac_of_peak": (traffic / (flood_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                "kernel": "flood_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernels": kernels,
+                "traffic_source": ktraffic.get("captured_at"),
                 "launch_ms": flood_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 # the same launch against the hardware instead of against the reference's 255 passes:
                 "dram_gbs": (traffic / (flood_avg_ms * 1e-3) / 1e9) if traffic else None,
-                "dram_frac_of_peak": (traffic / (flood_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "one_pass_bytes": one_pass, "one_pass_frac": one_pass / (flood_avg_ms * 1e-3) / 1e9 / peak,
                 "limiter": "issue rate of the in-tile relaxation (ncu: issue slots 66 % busy, 2.7 G warp instructions, "
                            "consumer warps wait 4 % for staged tiles); see profiles/r01_k_flood_kernel_*",

@@ -187,7 +187,10 @@ ws_status ws_transform_with_hook(ws_ctx *ctx, const ws_config *cfg,
 
 /* ---- WatershedUtils::pre_processor / pre_processor_with_max (lib.rs:1081-1173) -- */
 typedef enum ws_dtype {
-  WS_F32 = 0, WS_F64 = 1, WS_I32 = 2, WS_U16 = 3, WS_I16 = 4, WS_U8 = 5, WS_I64 = 6
+  WS_F32 = 0, WS_F64 = 1, WS_I32 = 2, WS_U16 = 3, WS_I16 = 4, WS_U8 = 5, WS_I64 = 6,
+  /* big-endian storage, swapped on the device: the data unit of a FITS file (BITPIX -32, -64, 16, 32, 64) goes
+   * up as it is on disk (tests/integration.rs:72-94 reads its cubes from FITS)                          */
+  WS_F32_BE = 7, WS_F64_BE = 8, WS_I16_BE = 9, WS_I32_BE = 10, WS_I64_BE = 11
 } ws_dtype;
 /* `n` elements of a standard-layout array of any dimension -> u8, exactly as the reference does it:
  * min/max folded from ZERO over the finite values (1147-1156); only values whose f64 image
@@ -363,6 +366,12 @@ ws_status ws_plan_forest_packets(ws_plan *plan, const void *d_packets, size_t n_
  * [0] state fill + seed colouring, [1] flood kernel, [2] parent + pointer jumping,
  * [3] merging (edges, union-find, counts; 0 for segmenting runs).            */
 ws_status ws_plan_phase_ms(ws_plan *plan, float out[4]);
+
+/* CUDA-event durations (ms) of the kernels of the last ws_plan_run, in launch order (0 where a kernel did not run):
+ * [0] fill_state (+ worklist reset), [1] seed_init, [2] flood, [3] label_tile, [4] rim_jump, [5] label_finish,
+ * [6] merge_reduce, [7] forest_init, [8] forest rounds, [9] lake counts.                                   */
+#define WS_KERNEL_SLOTS 10
+ws_status ws_plan_kernel_ms(ws_plan *plan, float out[WS_KERNEL_SLOTS]);
 
 /* ---- plain device-memory helpers for callers without a CUDA runtime of their own ---- */
 ws_status ws_dev_malloc(ws_ctx *ctx, size_t bytes, void **out);

@@ -119,6 +119,7 @@ SIGNATURES = {
     "ws_plan_forest_packets": (C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_uint8]),
     "ws_plan_stats": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8)]),
     "ws_plan_phase_ms": (C.c_int, [_P, C.POINTER(C.c_float * 4)]),
+    "ws_plan_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float * 10)]),
 }
 
 _lib = None
@@ -395,6 +396,14 @@ class Plan:
         arr = (C.c_float * 4)()
         self.ctx.check(self.lib.ws_plan_phase_ms(self.handle, C.byref(arr)))
         return {"init": arr[0], "flood": arr[1], "labels": arr[2], "merge": arr[3]}
+
+    KERNELS = ("fill_state", "seed_init", "flood", "label_tile", "rim_jump", "label_finish", "merge_reduce",
+               "forest_init", "forest_boruvka", "lake_counts")
+
+    def kernel_ms(self) -> dict:
+        arr = (C.c_float * 10)()
+        self.ctx.check(self.lib.ws_plan_kernel_ms(self.handle, C.byref(arr)))
+        return {k: float(arr[i]) for i, k in enumerate(self.KERNELS)}
 
     def stats(self) -> dict:
         arr = (C.c_uint64 * 8)()

@@ -90,6 +90,10 @@ struct ws_plan {
   bool tree_built = false;           // hook_to / hook_lvl hold the full merge tree of the last merging run
   uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // phase boundaries of the last run
+  // kernel boundaries of the last run: fill_state | seed_init | flood | label_tile | rim_jump | label_finish |
+  // merge_reduce | forest_init | forest rounds (or the level-ordered union) | lake counts |
+  cudaEvent_t kev[WS_KERNEL_SLOTS + 1] = {};
+  bool kev_valid[WS_KERNEL_SLOTS] = {};
 };
 
 namespace {
@@ -353,6 +357,8 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   if (e == cudaSuccess) e = flood_make_tensor_maps(p->fb, p->d, p->tmaps);
   for (auto& ev : p->ev)
     if (e == cudaSuccess) e = cudaEventCreate(&ev);
+  for (auto& ev : p->kev)
+    if (e == cudaSuccess) e = cudaEventCreate(&ev);
   if (e != cudaSuccess) {
     ws_plan_destroy(p);
     return cuda_fail(ctx, e, "ws_plan_create");
@@ -407,6 +413,8 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->d_total);
   if (p->h_ctrl) cudaFreeHost(p->h_ctrl);
   for (auto& ev : p->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto& ev : p->kev)
     if (ev) cudaEventDestroy(ev);
   delete p;
 }
@@ -523,6 +531,8 @@ static ws_status plan_merge(ws_plan* p) {
   // Per tile: FINAL forest edges (only counted) and DEFERRED edges between basins that reach the tile's rim.
   WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->seed_off, 1, p->mb.red_ab, p->mb.red_w,
                                    p->mb.red_count, s));
+  WS_CUDA(ctx, cudaEventRecord(p->kev[7], s));
+  p->kev_valid[6] = true;
 #ifdef WS_MERGE_STATS
   {
     uint32_t st[16];
@@ -537,17 +547,25 @@ static ws_status plan_merge(ws_plan* p) {
     WS_CUDA(ctx, launch_red_sort(p->mb.red_ab, p->mb.red_w, p->mb.red_count, 0, p->seed_off, p->d.n_img,
                                  p->mb.level_hist, p->mb.level_cursor, p->mb.fin_hist, p->mb.edges, s));
     WS_CUDA(ctx, launch_uf_init(p->mb, p->d, (uint32_t)p->nseeds, s));
+    WS_CUDA(ctx, cudaEventRecord(p->kev[8], s));
     WS_CUDA(ctx, launch_union_levels(p->mb, p->seed_off, p->d.n_img, lmax, ctx->union_grid, s));
+    WS_CUDA(ctx, cudaEventRecord(p->kev[9], s));
     WS_CUDA(ctx, launch_lake_counts(p->mb, p->d.n_img, lmax, s));
+    WS_CUDA(ctx, cudaEventRecord(p->kev[10], s));
+    for (int i = 7; i < 10; ++i) p->kev_valid[i] = true;
     p->stats[4] += 8;
   } else {
     // The forest of the DEFERRED graph by Boruvka rounds: every node is closed here (the list is the whole
     // graph), so every pick is a forest edge with its true level -- no order, no barrier per level.
     WS_TRY(plan_forest_buffers(p, p->nseeds, 0));
     WS_CUDA(ctx, launch_forest_init(p->fo, (uint32_t)p->nseeds, p->d.n_img, 0, ctx->sms, s));
+    WS_CUDA(ctx, cudaEventRecord(p->kev[8], s));
     WS_CUDA(ctx, launch_forest(p->fo, p->mb.red_ab, p->mb.red_w, p->mb.red_count, 1, 0, p->seed_off, p->d.n_img,
                                ctx->forest_grid, ctx->sms, s));
+    WS_CUDA(ctx, cudaEventRecord(p->kev[9], s));
     WS_CUDA(ctx, launch_forest_lake_counts(p->mb.ndistinct, p->fo, p->d.n_img, lmax, p->mb.counts, s));
+    WS_CUDA(ctx, cudaEventRecord(p->kev[10], s));
+    for (int i = 7; i < 10; ++i) p->kev_valid[i] = true;
     p->stats[4] += 5;
   }
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
@@ -596,15 +614,25 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   // hop counters can only overflow when a single slice has more than 2^24 pixels
   p->check_ovf = p->d.px_per_img() > (size_t)HOP_MASK ? 1 : 0;
   const int check_ovf = p->check_ovf;
+  for (auto& v : p->kev_valid) v = false;
   WS_CUDA(ctx, cudaEventRecord(p->ev[0], s));
+  WS_CUDA(ctx, cudaEventRecord(p->kev[0], s));
   WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_imgs, cfg->max_water_level, s));
+  WS_CUDA(ctx, cudaEventRecord(p->kev[1], s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, 0u, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[1], s));
+  WS_CUDA(ctx, cudaEventRecord(p->kev[2], s));
   p->bucket_shift = flood_bucket_shift(nseeds_total, p->d);
   WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
+  WS_CUDA(ctx, cudaEventRecord(p->kev[3], s));
   WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, cfg->tie_break == WS_TIE_RANDOM, ctx->tie_seed, s));
-  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, 1, s));
+  WS_CUDA(ctx, cudaEventRecord(p->kev[4], s));
+  WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, 0, s));
+  WS_CUDA(ctx, cudaEventRecord(p->kev[5], s));
+  WS_CUDA(ctx, launch_label_finish(p->fb, p->d, ctx->sms, s));
+  WS_CUDA(ctx, cudaEventRecord(p->kev[6], s));
+  for (int i = 0; i < 6; ++i) p->kev_valid[i] = true;
   WS_CUDA(ctx, cudaEventRecord(p->ev[3], s));
   p->stats[4] += 4 + (nseeds_total ? 1 : 0);
   if (cfg->kind == WS_MERGING) WS_TRY(plan_merge(p));
@@ -640,6 +668,11 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   return WS_OK;
 }
 
+namespace {  // (defined with the staged copies further down)
+ws_status copy_h2d(ws_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+ws_status copy_d2h(ws_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+}  // namespace
+
 extern "C" ws_status ws_dev_malloc(ws_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return WS_ERR_INVALID_ARG;
   *out = nullptr;
@@ -657,14 +690,14 @@ extern "C" ws_status ws_dev_free(ws_ctx* ctx, void* d_ptr) {
 extern "C" ws_status ws_memcpy_h2d(ws_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
   if (!ctx || (bytes && (!d_dst || !h_src))) return WS_ERR_INVALID_ARG;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
-  WS_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  WS_TRY(copy_h2d(ctx, d_dst, h_src, bytes));   // pageable memory goes through the page-locked ring
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return WS_OK;
 }
 extern "C" ws_status ws_memcpy_d2h(ws_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
   if (!ctx || (bytes && (!h_dst || !d_src))) return WS_ERR_INVALID_ARG;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
-  WS_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  WS_TRY(copy_d2h(ctx, h_dst, d_src, bytes));
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return WS_OK;
 }
@@ -1066,6 +1099,16 @@ extern "C" ws_status ws_plan_phase_ms(ws_plan* p, float out[4]) {
   return WS_OK;
 }
 
+extern "C" ws_status ws_plan_kernel_ms(ws_plan* p, float out[WS_KERNEL_SLOTS]) {
+  if (!p || !out) return WS_ERR_INVALID_ARG;
+  if (!p->ran) return fail(p->ctx, WS_ERR_INVALID_ARG, "no completed run");
+  for (int i = 0; i < WS_KERNEL_SLOTS; ++i) {
+    out[i] = 0.0f;
+    if (p->kev_valid[i]) WS_CUDA(p->ctx, cudaEventElapsedTime(&out[i], p->kev[i], p->kev[i + 1]));
+  }
+  return WS_OK;
+}
+
 extern "C" ws_status ws_plan_stats(ws_plan* p, uint64_t out[8]) {
   if (!p || !out) return WS_ERR_INVALID_ARG;
   for (int i = 0; i < 8; ++i) out[i] = p->stats[i];
@@ -1442,9 +1485,9 @@ ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint6
 
 static size_t dtype_size(int dtype) {
   switch (dtype) {
-    case WS_F32: case WS_I32: return 4;
-    case WS_F64: case WS_I64: return 8;
-    case WS_U16: case WS_I16: return 2;
+    case WS_F32: case WS_I32: case WS_F32_BE: case WS_I32_BE: return 4;
+    case WS_F64: case WS_I64: case WS_F64_BE: case WS_I64_BE: return 8;
+    case WS_U16: case WS_I16: case WS_I16_BE: return 2;
     case WS_U8: return 1;
   }
   return 0;

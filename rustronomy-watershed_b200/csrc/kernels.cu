@@ -9,6 +9,9 @@
 
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstring>
+
 namespace cg = cooperative_groups;
 
 namespace ws {
@@ -672,14 +675,40 @@ namespace ws {
 template <typename T>
 __device__ __forceinline__ double pp_to_f64(T v) { return (double)v; }
 
-template <typename T>
+// Element loads.  kSwap: the array holds big-endian values (the byte order of a FITS file), swapped on the way in,
+// so a cube's raw data unit goes to the device as it is on disk.
+template <typename T, bool kSwap>
+__device__ __forceinline__ T pp_load(const T* __restrict__ in, size_t i) {
+  if (!kSwap) return in[i];
+  if (sizeof(T) == 2) {
+    const uint16_t u = reinterpret_cast<const uint16_t*>(in)[i];
+    const uint16_t v = (uint16_t)((u >> 8) | (u << 8));
+    T out;
+    memcpy(&out, &v, 2);
+    return out;
+  } else if (sizeof(T) == 4) {
+    const uint32_t v = __byte_perm(reinterpret_cast<const uint32_t*>(in)[i], 0u, 0x0123);
+    T out;
+    memcpy(&out, &v, 4);
+    return out;
+  } else if (sizeof(T) == 8) {
+    const uint2 u = reinterpret_cast<const uint2*>(in)[i];
+    const uint2 v = make_uint2(__byte_perm(u.y, 0u, 0x0123), __byte_perm(u.x, 0u, 0x0123));
+    T out;
+    memcpy(&out, &v, 8);
+    return out;
+  }
+  return in[i];
+}
+
+template <typename T, bool kSwap>
 __global__ void __launch_bounds__(256) pp_minmax_kernel(const T* __restrict__ in, size_t n, T* __restrict__ part_min,
                                                         T* __restrict__ part_max) {
   __shared__ T s_min[256], s_max[256];
   T mn = (T)0, mx = (T)0;  // the fold starts at T::zero()
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const T x = in[i];
+    const T x = pp_load<T, kSwap>(in, i);
     const double f = pp_to_f64(x);
     const bool fin = !(isinf(f) || isnan(f));
     if (x < mn && fin) mn = x;
@@ -726,13 +755,13 @@ __global__ void __launch_bounds__(256) pp_finish_kernel(const T* __restrict__ pa
   }
 }
 
-template <typename T>
+template <typename T, bool kSwap>
 __global__ void __launch_bounds__(256) pp_map_kernel(const T* __restrict__ in, size_t n, const double* __restrict__ minmax,
                                                      double maxv, uint8_t* __restrict__ out) {
   const double mn = minmax[0], range = __dsub_rn(minmax[1], minmax[0]);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double f = pp_to_f64(in[i]);
+    const double f = pp_to_f64(pp_load<T, kSwap>(in, i));
     uint8_t v;
     const double a = fabs(f);
     const bool normal = a >= 2.2250738585072014e-308 && !isinf(f) && !isnan(f);  // f64::is_normal
@@ -748,19 +777,21 @@ __global__ void __launch_bounds__(256) pp_map_kernel(const T* __restrict__ in, s
   }
 }
 
-template <typename T>
+template <typename T, bool kSwap>
 static cudaError_t pp_run(const void* in, size_t n, uint32_t maxv, void* scratch, double* minmax, uint8_t* out,
                           cudaStream_t s) {
-  const int parts = 1024;
+  // enough CTAs for a cube, few enough that a 2048^2 slice is not all launch overhead
+  const int parts = (int)std::min<size_t>(1024, std::max<size_t>(1, (n + 4095) / 4096));
   T* pmin = (T*)scratch;
-  T* pmax = pmin + parts;
-  pp_minmax_kernel<T><<<parts, 256, 0, s>>>((const T*)in, n, pmin, pmax);
+  T* pmax = pmin + 1024;
+  pp_minmax_kernel<T, kSwap><<<parts, 256, 0, s>>>((const T*)in, n, pmin, pmax);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   pp_finish_kernel<T><<<1, 256, 0, s>>>(pmin, pmax, parts, minmax);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  pp_map_kernel<T><<<148 * 8, 256, 0, s>>>((const T*)in, n, minmax, (double)maxv, out);
+  const int maps = (int)std::min<size_t>(148 * 8, std::max<size_t>(1, (n + 1023) / 1024));
+  pp_map_kernel<T, kSwap><<<maps, 256, 0, s>>>((const T*)in, n, minmax, (double)maxv, out);
   return cudaGetLastError();
 }
 
@@ -769,13 +800,18 @@ size_t pre_processor_scratch_bytes() { return 2 * 1024 * 8; }
 cudaError_t launch_pre_processor(int dtype, const void* in, size_t n, uint32_t maxv, void* scratch, double* minmax,
                                  uint8_t* out, cudaStream_t s) {
   switch (dtype) {
-    case 0: return pp_run<float>(in, n, maxv, scratch, minmax, out, s);
-    case 1: return pp_run<double>(in, n, maxv, scratch, minmax, out, s);
-    case 2: return pp_run<int32_t>(in, n, maxv, scratch, minmax, out, s);
-    case 3: return pp_run<uint16_t>(in, n, maxv, scratch, minmax, out, s);
-    case 4: return pp_run<int16_t>(in, n, maxv, scratch, minmax, out, s);
-    case 5: return pp_run<uint8_t>(in, n, maxv, scratch, minmax, out, s);
-    case 6: return pp_run<long long>(in, n, maxv, scratch, minmax, out, s);
+    case 0: return pp_run<float, false>(in, n, maxv, scratch, minmax, out, s);
+    case 1: return pp_run<double, false>(in, n, maxv, scratch, minmax, out, s);
+    case 2: return pp_run<int32_t, false>(in, n, maxv, scratch, minmax, out, s);
+    case 3: return pp_run<uint16_t, false>(in, n, maxv, scratch, minmax, out, s);
+    case 4: return pp_run<int16_t, false>(in, n, maxv, scratch, minmax, out, s);
+    case 5: return pp_run<uint8_t, false>(in, n, maxv, scratch, minmax, out, s);
+    case 6: return pp_run<long long, false>(in, n, maxv, scratch, minmax, out, s);
+    case 7: return pp_run<float, true>(in, n, maxv, scratch, minmax, out, s);      // big-endian (FITS BITPIX -32)
+    case 8: return pp_run<double, true>(in, n, maxv, scratch, minmax, out, s);     // BITPIX -64
+    case 9: return pp_run<int16_t, true>(in, n, maxv, scratch, minmax, out, s);    // BITPIX 16
+    case 10: return pp_run<int32_t, true>(in, n, maxv, scratch, minmax, out, s);   // BITPIX 32
+    case 11: return pp_run<long long, true>(in, n, maxv, scratch, minmax, out, s); // BITPIX 64
     default: return cudaErrorInvalidValue;
   }
 }
