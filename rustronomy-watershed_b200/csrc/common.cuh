@@ -67,6 +67,11 @@ struct ImageDims {
   __host__ __device__ size_t pix_plane() const { return (size_t)pix_pitch() * pix_rows(); }
 };
 
+// SMs of the device the library runs on (streaming grids are sized in multiples of it); 148 on a B200, set from
+// the device attributes when a context is created.
+int num_sms();
+void set_num_sms(int n);
+
 __device__ __forceinline__ uint32_t ld_cg(const uint32_t* p) { return __ldcg(p); }
 // Polling load: relaxed, GPU scope, with a memory clobber.  __ldcg is an `asm volatile` WITHOUT the
 // clobber, and nvcc hoists it out of a spin loop as loop-invariant (seen in SASS: one LDG followed by a

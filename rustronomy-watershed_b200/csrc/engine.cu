@@ -237,6 +237,7 @@ extern "C" ws_status ws_ctx_create(int device, ws_ctx** out) {
   c->union_grid = union_max_grid(device);
   c->forest_grid = forest_max_grid(device);
   cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
+  set_num_sms(c->sms);
   if (c->flood_grid <= 0 || c->jump_grid <= 0 || c->union_grid <= 0 || c->forest_grid <= 0) {
     cudaGetLastError();
     ws_ctx_destroy(c);
@@ -338,6 +339,8 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->fb.qslots, (size_t)FLOOD_BUCKETS * p->fb.qcap * 4);
   alloc((void**)&p->fb.qmask, ntiles * 8);
   alloc((void**)&p->fb.ctrl, FC_WORDS * 4);
+  alloc((void**)&p->fb.row_start, (n_img * rows + 1) * 4);
+  alloc((void**)&p->fb.rowbase, n_img * rows * 2 * (size_t)p->d.tiles_x * 4);
   alloc((void**)&p->mb.level_hist, 257 * 4);
   alloc((void**)&p->mb.level_cursor, 256 * 4);
   alloc((void**)&p->mb.red_count, 64);
@@ -384,6 +387,8 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->fb.qslots);
   cudaFree(p->fb.qmask);
   cudaFree(p->fb.ctrl);
+  cudaFree(p->fb.row_start);
+  cudaFree(p->fb.rowbase);
   cudaFree(p->mb.level_hist);
   cudaFree(p->mb.level_cursor);
   cudaFree(p->mb.edges);
@@ -617,7 +622,10 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   for (auto& v : p->kev_valid) v = false;
   WS_CUDA(ctx, cudaEventRecord(p->ev[0], s));
   WS_CUDA(ctx, cudaEventRecord(p->kev[0], s));
-  WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_imgs, cfg->max_water_level, s));
+  p->fb.seed_off = d_seed_off;
+  p->fb.colour_base = 0u;
+  WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_imgs, cfg->max_water_level, d_seeds_rc, d_seed_off,
+                                 (uint32_t)nseeds_total, ctx->sms, s));
   WS_CUDA(ctx, cudaEventRecord(p->kev[1], s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, d_seed_off, (uint32_t)nseeds_total, 0u, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[1], s));
@@ -828,7 +836,10 @@ static ws_status strip_begin_impl(ws_plan* p, const ws_config* cfg, const ws_str
   WS_CUDA(ctx, cudaMemcpyAsync(p->d_strip_off, p->h_ctrl + FC_WORDS + 8, 8, cudaMemcpyHostToDevice, s));
   // hop counters cross strip boundaries through the halo exchange: the WHOLE field decides
   p->check_ovf = (size_t)st->global_rows * (size_t)p->d.cols > (size_t)HOP_MASK ? 1 : 0;
-  WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_img, cfg->max_water_level, s));
+  p->fb.seed_off = p->d_strip_off;
+  p->fb.colour_base = st->colour_base;
+  WS_CUDA(ctx, launch_fill_state(p->fb, p->d, d_img, cfg->max_water_level, d_seeds_rc, p->d_strip_off, (uint32_t)nseeds,
+                                 ctx->sms, s));
   WS_CUDA(ctx, launch_seed_init(p->fb, p->d, d_seeds_rc, p->d_strip_off, (uint32_t)nseeds, st->colour_base, s));
   p->bucket_shift = flood_bucket_shift(nseeds, p->d);
   WS_CUDA(ctx, launch_flood(p->fb, p->d, p->check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
@@ -1536,25 +1547,16 @@ extern "C" ws_status ws_pre_processor(ws_ctx* ctx, ws_dtype dtype, const void* d
   return st;
 }
 
-extern "C" ws_status ws_find_local_minima_batch(ws_ctx* ctx, const uint8_t* imgs, size_t n_img, size_t rows,
-                                                size_t cols, uint64_t** out_rc, uint64_t* out_offsets) {
-  if (!ctx || !imgs || !out_rc || !out_offsets) return WS_ERR_INVALID_ARG;
-  *out_rc = nullptr;
-  WS_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (n_img == 0 || rows == 0 || cols == 0) return fail(ctx, WS_ERR_INVALID_ARG, "empty image");
-  ws_plan* p = nullptr;
-  WS_TRY(get_plan(ctx, n_img, rows, cols, &p));
+// find_local_minima of n_img dense slices already on the device (ctx->d_img) -> library-owned host list
+static ws_status minima_from_device(ws_ctx* ctx, ws_plan* p, size_t n_img, uint64_t** out_rc, uint64_t* out_offsets) {
   cudaStream_t s = ctx->stream;
-  const size_t npx = n_img * rows * cols;
-  WS_TRY(grow(ctx, ctx->d_img, ctx->d_img_cap, npx));
-  WS_CUDA(ctx, cudaMemcpyAsync(ctx->d_img, imgs, npx, cudaMemcpyHostToDevice, s));
   WS_TRY(grow(ctx, ctx->d_seed_off, ctx->d_seed_off_cap, n_img + 1));
   size_t total = 0;
   WS_TRY(ws_plan_find_local_minima(p, ctx->d_img, nullptr, 0, ctx->d_seed_off, &total));
   WS_TRY(grow(ctx, ctx->d_seeds, ctx->d_seeds_cap, 2 * total));
   if (total) WS_CUDA(ctx, launch_minima_write(ctx->d_img, p->d, p->chunk_counts, ctx->d_seeds, (uint32_t)total, s));
   std::vector<uint32_t> h(2 * std::max<size_t>(total, 1)), hoff(n_img + 1);
-  if (total) WS_CUDA(ctx, cudaMemcpyAsync(h.data(), ctx->d_seeds, 2 * total * 4, cudaMemcpyDeviceToHost, s));
+  if (total) WS_TRY(copy_d2h(ctx, h.data(), ctx->d_seeds, 2 * total * 4));
   WS_CUDA(ctx, cudaMemcpyAsync(hoff.data(), ctx->d_seed_off, (n_img + 1) * 4, cudaMemcpyDeviceToHost, s));
   WS_CUDA(ctx, cudaStreamSynchronize(s));
   uint64_t* out = (uint64_t*)malloc(std::max<size_t>(2 * total, 1) * sizeof(uint64_t));
@@ -1565,23 +1567,32 @@ extern "C" ws_status ws_find_local_minima_batch(ws_ctx* ctx, const uint8_t* imgs
   return WS_OK;
 }
 
+extern "C" ws_status ws_find_local_minima_batch(ws_ctx* ctx, const uint8_t* imgs, size_t n_img, size_t rows,
+                                                size_t cols, uint64_t** out_rc, uint64_t* out_offsets) {
+  if (!ctx || !imgs || !out_rc || !out_offsets) return WS_ERR_INVALID_ARG;
+  *out_rc = nullptr;
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n_img == 0 || rows == 0 || cols == 0) return fail(ctx, WS_ERR_INVALID_ARG, "empty image");
+  ws_plan* p = nullptr;
+  WS_TRY(get_plan(ctx, n_img, rows, cols, &p));
+  const size_t npx = n_img * rows * cols;
+  WS_TRY(grow(ctx, ctx->d_img, ctx->d_img_cap, npx));
+  WS_TRY(copy_h2d(ctx, ctx->d_img, imgs, npx));
+  return minima_from_device(ctx, p, n_img, out_rc, out_offsets);
+}
+
 extern "C" ws_status ws_find_local_minima(ws_ctx* ctx, const ws_image* img, uint64_t** out_rc, size_t* out_n) {
   if (!ctx || !out_rc || !out_n) return WS_ERR_INVALID_ARG;
   *out_rc = nullptr;
   *out_n = 0;
   WS_TRY(check_image(ctx, img));
-  const bool dense = img->col_stride == 1 && img->row_stride == (ptrdiff_t)img->cols;
-  std::vector<uint8_t> tmp;
-  const uint8_t* src = img->data;
-  if (!dense) {
-    tmp.resize(img->rows * img->cols);
-    for (size_t r = 0; r < img->rows; ++r)
-      for (size_t c = 0; c < img->cols; ++c)
-        tmp[r * img->cols + c] = img->data[(ptrdiff_t)r * img->row_stride + (ptrdiff_t)c * img->col_stride];
-    src = tmp.data();
-  }
+  WS_CUDA(ctx, cudaSetDevice(ctx->device));
+  ws_plan* p = nullptr;
+  WS_TRY(get_plan(ctx, 1, img->rows, img->cols, &p));
+  WS_TRY(grow(ctx, ctx->d_img, ctx->d_img_cap, img->rows * img->cols));
+  WS_TRY(upload_image(ctx, img, ctx->d_img));   // any strides: dense on the device (the workers gather, hostpipe.h)
   uint64_t off[2] = {0, 0};
-  WS_TRY(ws_find_local_minima_batch(ctx, src, 1, img->rows, img->cols, out_rc, off));
+  WS_TRY(minima_from_device(ctx, p, 1, out_rc, off));
   *out_n = (size_t)off[1];
   return WS_OK;
 }

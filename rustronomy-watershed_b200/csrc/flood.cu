@@ -62,6 +62,7 @@ __device__ __forceinline__ bool consumer_sync_or(bool pred) {
 // before that are the seeds' own (written by seed_init).
 __global__ void __launch_bounds__(256) fill_state_kernel(FloodBuffers b, ImageDims d, const uint8_t* __restrict__ img,
                                                          uint32_t lmax) {
+  if (ld_cg(&b.ctrl[FC_SEED_UNSORTED]) == 0u) return;  // fill_rows_kernel has done it
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   // arrival times: the padded plane is a multiple of 8 words
@@ -93,18 +94,6 @@ __global__ void __launch_bounds__(256) fill_state_kernel(FloodBuffers b, ImageDi
     }
     P4[i] = make_uchar4((unsigned char)v[0], (unsigned char)v[1], (unsigned char)v[2], (unsigned char)v[3]);
   }
-}
-
-cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, cudaStream_t s) {
-  fill_state_kernel<<<148 * 16, 256, 0, s>>>(b, d, img, lmax);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  // empty worklist: all ring slots unwritten, no tile queued, counters zero
-  e = cudaMemsetAsync(b.qslots, 0xFF, sizeof(uint32_t) * (size_t)FLOOD_BUCKETS * b.qcap, s);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(b.qmask, 0, sizeof(unsigned long long) * (size_t)d.tiles_total(), s);
-  if (e != cudaSuccess) return e;
-  return cudaMemsetAsync(b.ctrl, 0, sizeof(uint32_t) * FC_WORDS, s);
 }
 
 constexpr uint32_t TILE_NONE_U = 0xFFFFFFFFu;
@@ -159,6 +148,148 @@ __device__ __forceinline__ void push_tile(const FloodBuffers& b, uint32_t tile, 
   }
 }
 
+// ---- sorted seed lists -----------------------------------------------------------------------------
+// find_local_minima returns its seeds in row-major order without repeats.  For such a list nothing has to be
+// scattered: a CTA per image row writes the row of T once (INF, then 0 at the row's seeds while the lines are
+// still in L2), the colour of a seed is its position in the list -- label_tile derives it from rowbase[] and the
+// seeds to its left in the tile row -- and the label plane is not touched at all.  (The general path below
+// rewrites nearly every 32-byte sector of T and of the label plane a second time: 3.1 GB of DRAM traffic for
+// 29 M seeds.)  A list that is not strictly ascending, or has a seed outside the image, takes the general path.
+
+__device__ __forceinline__ int seed_slice_of(const uint32_t* __restrict__ seed_off, int n_img, uint32_t i) {
+  int lo = 0, hi = n_img;  // last b with seed_off[b] <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// sets FC_SEED_UNSORTED on a violation; writes row_start[] (meaningful only when the list is sorted)
+__global__ void __launch_bounds__(256) seeds_scan_kernel(FloodBuffers b, ImageDims d,
+                                                         const uint32_t* __restrict__ seeds_rc,
+                                                         const uint32_t* __restrict__ seed_off, uint32_t nseeds) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nseeds; i += stride) {
+    const int img = seed_slice_of(seed_off, d.n_img, i);
+    const uint2 rc = __ldg(reinterpret_cast<const uint2*>(seeds_rc) + i);
+    const uint32_t first = __ldg(seed_off + img), end = __ldg(seed_off + img + 1);
+    bool bad = rc.x >= (uint32_t)d.rows || rc.y >= (uint32_t)d.cols;
+    int prev_row = -1;
+    if (i > first) {
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(seeds_rc) + i - 1);
+      bad |= !(q.x < rc.x || (q.x == rc.x && q.y < rc.y));
+      prev_row = (int)min(q.x, (uint32_t)d.rows - 1u);
+    }
+    if (bad) {
+      st_cg(&b.ctrl[FC_SEED_UNSORTED], 1u);
+      continue;
+    }
+    uint32_t* rs = b.row_start + (size_t)img * d.rows;
+    for (int r = prev_row + 1; r <= (int)rc.x; ++r) rs[r] = i;        // rows without seeds point at the next seed
+    if (i + 1 == end)
+      for (int r = (int)rc.x + 1; r < d.rows; ++r) rs[r] = end;
+  }
+}
+// slices without a single seed, and the sentinel behind the last row
+__global__ void __launch_bounds__(256) seeds_scan_empty_kernel(FloodBuffers b, ImageDims d,
+                                                               const uint32_t* __restrict__ seed_off, uint32_t nseeds) {
+  const int img = blockIdx.x;
+  if (img == 0 && threadIdx.x == 0) b.row_start[(size_t)d.n_img * d.rows] = nseeds;
+  const uint32_t first = __ldg(seed_off + img);
+  if (first != __ldg(seed_off + img + 1)) return;
+  for (int r = threadIdx.x; r < d.rows; r += blockDim.x) b.row_start[(size_t)img * d.rows + r] = first;
+}
+
+// one CTA per row of the padded arrival-time plane
+__global__ void __launch_bounds__(256) fill_rows_kernel(FloodBuffers b, ImageDims d, const uint8_t* __restrict__ img,
+                                                        uint32_t lmax, const uint32_t* __restrict__ seeds_rc) {
+  if (ld_cg(&b.ctrl[FC_SEED_UNSORTED]) != 0u) return;
+  const int t_rows = d.t_rows(), pitch = d.t_pitch();
+  const int im = blockIdx.x / t_rows, prow = blockIdx.x - im * t_rows;
+  const int r = prow - 1;  // image row of this padded row
+  uint32_t* Trow = b.T + (size_t)im * d.t_plane() + (size_t)prow * pitch;
+  const uint4 inf4 = make_uint4(T_INF, T_INF, T_INF, T_INF);
+  for (int i = threadIdx.x; i < pitch / 4; i += blockDim.x) __stcg(reinterpret_cast<uint4*>(Trow) + i, inf4);
+  if (r < 0 || r >= d.pix_rows()) return;
+  {  // the image row re-encoded for the flood: 255 = never floods (border, above the last level, padding)
+    const int ppitch = d.pix_pitch();
+    uchar4* P4 = reinterpret_cast<uchar4*>(b.pix + (size_t)im * d.pix_plane() + (size_t)r * ppitch);
+    const bool inner = r >= 1 && r <= d.rows - 2;
+    const uint8_t* row = img + (size_t)im * d.px_per_img() + (size_t)r * d.cols;
+    for (int i = threadIdx.x; i < ppitch / 4; i += blockDim.x) {
+      uint32_t v[4] = {255u, 255u, 255u, 255u};
+      if (inner) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = 4 * i + k;
+          if (c >= 1 && c <= d.cols - 2) {
+            const uint32_t x = __ldg(row + c);
+            v[k] = x > lmax ? 255u : x;
+          }
+        }
+      }
+      P4[i] = make_uchar4((unsigned char)v[0], (unsigned char)v[1], (unsigned char)v[2], (unsigned char)v[3]);
+    }
+  }
+  if (r >= d.rows) return;
+  __syncthreads();  // the row of T is written: the seeds' zeros go on top of it
+  const uint32_t lo = b.row_start[(size_t)im * d.rows + r], hi = b.row_start[(size_t)im * d.rows + r + 1];
+  const int ty = r / TILE_H;
+  const uint32_t tile0 = (uint32_t)im * d.tiles_per_img() + (uint32_t)ty * d.tiles_x;
+  for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+    const uint32_t c = __ldg(seeds_rc + 2 * (size_t)j + 1);
+    st_cg(Trow + c + T_PAD_L, 0u);
+    // queue the tiles that must look at this seed (red-black order as in seed_init; the flood is a later launch)
+    const int tx = (int)c / TILE_W;
+    const uint32_t tile = tile0 + (uint32_t)tx;
+    const uint32_t par = (uint32_t)(tx + ty) & 1u;
+    const bool first_of_tile = j == lo || (int)__ldg(seeds_rc + 2 * (size_t)j - 1) / TILE_W != tx;
+    if (first_of_tile) {
+      push_tile<true>(b, tile, par);
+      if (r % TILE_H == 0 && ty > 0) push_tile<true>(b, tile - d.tiles_x, par ^ 1u);
+      if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile<true>(b, tile + d.tiles_x, par ^ 1u);
+    }
+    if (c % TILE_W == 0 && tx > 0) push_tile<true>(b, tile - 1, par ^ 1u);
+    if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile<true>(b, tile + 1, par ^ 1u);
+  }
+  // rowbase: index of the first seed of this row at or right of every 32-column block's first column
+  for (int t = threadIdx.x; t < 2 * d.tiles_x; t += blockDim.x) {
+    uint32_t a = lo, z = hi;
+    const uint32_t want = (uint32_t)t * (TILE_W / 2);
+    while (a < z) {
+      const uint32_t mid = (a + z) >> 1;
+      if (__ldg(seeds_rc + 2 * (size_t)mid + 1) < want) a = mid + 1; else z = mid;
+    }
+    b.rowbase[((size_t)im * d.rows + r) * (2 * d.tiles_x) + t] = a;
+  }
+}
+
+cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, const uint32_t* seeds_rc,
+                              const uint32_t* seed_off, uint32_t nseeds, int sms, cudaStream_t s) {
+  // empty worklist: all ring slots unwritten, no tile queued, counters zero
+  cudaError_t e = cudaMemsetAsync(b.qslots, 0xFF, sizeof(uint32_t) * (size_t)FLOOD_BUCKETS * b.qcap, s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(b.qmask, 0, sizeof(unsigned long long) * (size_t)d.tiles_total(), s);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(b.ctrl, 0, sizeof(uint32_t) * FC_WORDS, s);
+  if (e != cudaSuccess) return e;
+  if (nseeds) {
+    const uint32_t want = (nseeds + 255) / 256, cap = (uint32_t)sms * 32u;
+    seeds_scan_kernel<<<want < cap ? want : cap, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  seeds_scan_empty_kernel<<<d.n_img, 256, 0, s>>>(b, d, seed_off, nseeds);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  fill_rows_kernel<<<d.n_img * d.t_rows(), 256, 0, s>>>(b, d, img, lmax, seeds_rc);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  fill_state_kernel<<<sms * 16, 256, 0, s>>>(b, d, img, lmax);   // (returns at once unless the list is unsorted)
+  return cudaGetLastError();
+}
+
 // Colour the starting pixels (lib.rs:1365-1367): T = 0, colour = index + 1, a later duplicate overwrites an
 // earlier one (sequential loop) == the largest index wins.  The label plane is not cleared beforehand, so the
 // colour is a plain store; a position that occurs twice shows up as an exchange on T that returns 0, and
@@ -168,6 +299,7 @@ __global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDim
                                                         const uint32_t* __restrict__ seeds_rc,
                                                         const uint32_t* __restrict__ seed_off, uint32_t nseeds,
                                                         uint32_t colour_base) {
+  if (ld_cg(&b.ctrl[FC_SEED_UNSORTED]) == 0u) return;  // sorted list: fill_rows_kernel has placed the seeds
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t tile = TILE_NONE_U, par = 0;
   uint32_t r = 0, c = 0;
@@ -216,7 +348,7 @@ __global__ void __launch_bounds__(256) seed_dup_kernel(FloodBuffers b, ImageDims
                                                        const uint32_t* __restrict__ seeds_rc,
                                                        const uint32_t* __restrict__ seed_off, uint32_t nseeds,
                                                        uint32_t colour_base) {
-  if (ld_cg(&b.ctrl[FC_SEED_DUP]) == 0u) return;
+  if (ld_cg(&b.ctrl[FC_SEED_UNSORTED]) == 0u || ld_cg(&b.ctrl[FC_SEED_DUP]) == 0u) return;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nseeds; i += stride) {
     int lo = 0, hi = d.n_img;
@@ -260,7 +392,8 @@ cudaError_t launch_seeds_convert(const uint64_t* in, uint32_t* out, size_t nseed
   if (nseeds == 0) return cudaSuccess;
   const size_t n2 = 2 * nseeds;
   const size_t want = (n2 + 255) / 256;
-  const unsigned grid = (unsigned)(want < (size_t)148 * 8 ? want : (size_t)148 * 8);
+  const size_t gcap = (size_t)num_sms() * 8;
+  const unsigned grid = (unsigned)(want < gcap ? want : gcap);
   seeds_convert_kernel<<<grid, 256, 0, s>>>(in, out, n2, rows, cols);
   return cudaGetLastError();
 }
@@ -926,7 +1059,7 @@ cudaError_t launch_strip_import_lab(FloodBuffers b, ImageDims d, int row, const 
 }
 cudaError_t launch_strip_count_pending(const uint32_t* lab, ImageDims d, int r0, int r1, uint32_t* ctrl,
                                        cudaStream_t s) {
-  strip_count_pending_kernel<<<148 * 4, 256, 0, s>>>(lab, d, r0, r1, ctrl);
+  strip_count_pending_kernel<<<num_sms() * 4, 256, 0, s>>>(lab, d, r0, r1, ctrl);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,10 @@ namespace cg = cooperative_groups;
 
 namespace ws {
 
+static int g_num_sms = 148;
+int num_sms() { return g_num_sms; }
+void set_num_sms(int n) { if (n > 0) g_num_sms = n; }
+
 // ===========================================================================
 // K1  find_local_minima  (lib.rs:1178-1197)
 //
@@ -493,7 +497,7 @@ __global__ void __launch_bounds__(256) snapshot_kernel(const uint32_t* __restric
 
 static unsigned stream_grid(size_t n) {
   const size_t want = (n + 255) / 256;
-  const size_t cap = (size_t)148 * 16;
+  const size_t cap = (size_t)num_sms() * 16;
   return (unsigned)(want < cap ? (want ? want : 1) : cap);
 }
 
@@ -790,7 +794,7 @@ static cudaError_t pp_run(const void* in, size_t n, uint32_t maxv, void* scratch
   pp_finish_kernel<T><<<1, 256, 0, s>>>(pmin, pmax, parts, minmax);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int maps = (int)std::min<size_t>(148 * 8, std::max<size_t>(1, (n + 1023) / 1024));
+  const int maps = (int)std::min<size_t>((size_t)num_sms() * 8, std::max<size_t>(1, (n + 1023) / 1024));
   pp_map_kernel<T, kSwap><<<maps, 256, 0, s>>>((const T*)in, n, minmax, (double)maxv, out);
   return cudaGetLastError();
 }

@@ -21,7 +21,10 @@ enum FloodCtrl {
   FC_JUMP_ROUNDS = 12,
   FC_STRIP_CHANGED = 13,  // a halo row of arrival times got lower on import
   FC_STRIP_PENDING = 14,  // owned pixels whose label is still a pointer
-  FC_OUTSTANDING = 15,    // worklist entries queued or being processed; the flood ends when it reaches 0
+  FC_OUTSTANDING = 15,
+  FC_SEED_UNSORTED = 24,  // the seed list is not strictly ascending in (slice, row, column), or holds a seed outside
+                          // the image: init takes the general path (seed_init) and label_tile reads the seeds'
+                          // colours from the label plane instead of deriving them from the list order    // worklist entries queued or being processed; the flood ends when it reaches 0
   FC_QAVAIL0 = 64,        // [64]  per bucket: entries fully published and not yet claimed (a semaphore)
   FC_QHEAD0 = 128,        // [64]  per bucket: next slot to hand out
   FC_QTAIL0 = 192,        // [64]  per bucket: next slot to fill
@@ -46,6 +49,11 @@ struct FloodBuffers {
   unsigned long long* qmask;  // [tiles_total] bit b: an entry for the tile sits in bucket b; bit 63: Q_DIRTY
   uint32_t* ctrl;    // [FC_WORDS]
   uint32_t qcap;     // slots per ring = tiles_total + FLOOD_QSLACK
+  // sorted seed lists (what find_local_minima returns): colours follow from the order, nothing is scattered
+  uint32_t* row_start;        // [n_img * rows + 1] index of the first seed at or after (slice, row)
+  uint32_t* rowbase;          // [n_img * rows][2 * tiles_x] index of the first seed of the row at or right of a 32-column block
+  const uint32_t* seed_off;   // [n_img + 1] of the current run
+  uint32_t colour_base;       // strips: colour of local seed i = colour_base + i + 1
 };
 constexpr uint32_t FLOOD_QSLACK = 4096;  // > CTAs that can sit between claiming a slot and clearing it
 
@@ -66,7 +74,10 @@ cudaError_t launch_minima_write(const uint8_t* img, ImageDims d, const uint32_t*
                                 uint32_t* out_rc, uint32_t cap, cudaStream_t s);
 
 // --- flood (find_flooded_px + write-back over all levels, lib.rs:196-257, 1379-1438) ---
-cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, cudaStream_t s);
+// state of a run: arrival times, flood image, empty worklist, and -- when the seed list is sorted -- the seeds
+// themselves (launch_seed_init then returns at once)
+cudaError_t launch_fill_state(FloodBuffers b, ImageDims d, const uint8_t* img, uint32_t lmax, const uint32_t* seeds_rc,
+                              const uint32_t* seed_off, uint32_t nseeds, int sms, cudaStream_t s);
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
                              uint32_t nseeds, uint32_t colour_base, cudaStream_t s);
 // row-strip decomposition: boundary rows of arrival times / labels (flood.cu)

@@ -89,6 +89,10 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   const int lc = tid % TILE_W, g = tid / TILE_W;
   const size_t base = (size_t)img * d.px_per_img();
   const uint32_t rim_total = (uint32_t)d.tiles_total() * RIM_PER_TILE;
+  // Sorted seed list (flood.cu, fill_rows_kernel): a seed's colour is its position in the list -- the index of
+  // the row's first seed at or right of this warp's first column (rowbase, one entry per 32 columns), plus the
+  // seeds to its left among the warp's 32 columns (a warp holds one row, 32 consecutive columns, per step).
+  const bool sorted = __ldcg(&b.ctrl[FC_SEED_UNSORTED]) == 0u;
   int nseed_px = 0;  // owned pixels that hold a seed (arrival time 0): the colours present on the canvas
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
@@ -96,9 +100,11 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
     const int li = lr * TILE_W + lc;
     const int r = r0 + lr, c = c0 + lc;
     uint32_t term = LAB_RESOLVED;  // UNCOLOURED
-    if (r < d.rows && c < d.cols) {
-      const uint32_t* t = sm.T + (lr + 1) * LT_W + lc + LT_C0;
-      const uint32_t tv = t[0];
+    const uint32_t* t = sm.T + (lr + 1) * LT_W + lc + LT_C0;
+    const uint32_t tv = t[0];
+    const bool inside = r < d.rows && c < d.cols;
+    const uint32_t seeds_here = __ballot_sync(0xffffffffu, inside && tv == 0u && !d.is_halo_row(r));
+    if (inside) {
       const size_t p = base + (size_t)r * d.cols + c;
       b.lvl[p] = (tv >= T_INF) ? (uint8_t)255 : (uint8_t)(tv >> 24);
       if (d.is_halo_row(r)) {
@@ -110,7 +116,13 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
       } else if (tv >= T_INF) {
         // never coloured
       } else if (tv == 0u) {
-        term = __ldcg(b.lab + p);  // seed: coloured by seed_init
+        if (sorted) {
+          const uint32_t left = (uint32_t)__popc(seeds_here & ((1u << (lc & 31)) - 1u));
+          const uint32_t idx = __ldg(b.rowbase + ((size_t)img * d.rows + r) * (2 * d.tiles_x) + 2 * tx + (lc >> 5)) + left;
+          term = LAB_RESOLVED | (b.colour_base + idx - __ldg(b.seed_off + img) + 1u);
+        } else {
+          term = __ldcg(b.lab + p);  // seed: coloured by seed_init
+        }
         ++nseed_px;
       } else {
         // A coloured non-seed pixel is interior, so all four neighbours exist.
@@ -293,7 +305,8 @@ cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, int finish, cudaS
   if (e != cudaSuccess || !finish) return e;
   const size_t n = d.px_total();
   const size_t w2 = (n / 4 + 255) / 256;
-  const unsigned g2 = (unsigned)(w2 < (size_t)148 * 16 ? (w2 ? w2 : 1) : (size_t)148 * 16);
+  const size_t g2cap = (size_t)num_sms() * 16;
+  const unsigned g2 = (unsigned)(w2 < g2cap ? (w2 ? w2 : 1) : g2cap);
   label_finish_kernel<<<g2, 256, 0, s>>>(b.lab, n, rim);
   return cudaGetLastError();
 }

@@ -446,13 +446,13 @@ cudaError_t launch_red_sort(const uint2* red_ab, const uint8_t* red_w, const uin
     e = cudaMemsetAsync(fin_hist, 0, sizeof(uint32_t) * 256 * (size_t)n_img, s);
     if (e != cudaSuccess) return e;
   }
-  red_hist_kernel<<<148 * 8, 256, 0, s>>>(red_ab, red_w, red_count, all, seed_off, n_img, level_hist, fin_hist);
+  red_hist_kernel<<<num_sms() * 8, 256, 0, s>>>(red_ab, red_w, red_count, all, seed_off, n_img, level_hist, fin_hist);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   edge_scan_kernel<<<1, 256, 0, s>>>(level_hist, level_cursor);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  red_scatter_kernel<<<148 * 8, 256, 0, s>>>(red_ab, red_w, red_count, all, level_cursor, edges);
+  red_scatter_kernel<<<num_sms() * 8, 256, 0, s>>>(red_ab, red_w, red_count, all, level_cursor, edges);
   return cudaGetLastError();
 }
 
