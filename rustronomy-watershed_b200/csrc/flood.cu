@@ -210,7 +210,37 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(FloodBuffers b, ImageDim
   const int r = prow - 1;  // image row of this padded row
   uint32_t* Trow = b.T + (size_t)im * d.t_plane() + (size_t)prow * pitch;
   const uint4 inf4 = make_uint4(T_INF, T_INF, T_INF, T_INF);
-  for (int i = threadIdx.x; i < pitch / 4; i += blockDim.x) __stcg(reinterpret_cast<uint4*>(Trow) + i, inf4);
+  // Rows with seeds: a bitmap of the seeds' columns in shared memory, then every word of the row is written once
+  // (INF first and the zeros on top of it later made the lines travel twice: 1.1 GB read + 0.6 GB extra written).
+  constexpr int FR_COLS = 32768;                    // columns per pass: 4 KB of bitmap
+  __shared__ uint32_t s_bits[FR_COLS / 32];
+  const bool image_row = r >= 0 && r < d.rows;
+  uint32_t lo = 0, hi = 0;
+  if (image_row) {
+    lo = b.row_start[(size_t)im * d.rows + r];
+    hi = b.row_start[(size_t)im * d.rows + r + 1];
+  }
+  if (lo == hi) {
+    for (int i = threadIdx.x; i < pitch / 4; i += blockDim.x) __stcg(reinterpret_cast<uint4*>(Trow) + i, inf4);
+  } else {
+    // padded column p holds image column p - T_PAD_L
+    for (int p0 = 0; p0 < pitch; p0 += FR_COLS) {
+      const int np = min(FR_COLS, pitch - p0);      // a multiple of 8
+      for (int i = threadIdx.x; i < (np + 31) / 32; i += blockDim.x) s_bits[i] = 0u;
+      __syncthreads();
+      for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
+        const int p = (int)__ldg(seeds_rc + 2 * (size_t)j + 1) + T_PAD_L - p0;
+        if (p >= 0 && p < np) atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < np / 4; i += blockDim.x) {
+        const uint32_t m = (s_bits[i >> 3] >> ((i & 7) * 4)) & 0xFu;
+        __stcg(reinterpret_cast<uint4*>(Trow + p0) + i,
+               make_uint4((m & 1u) ? 0u : T_INF, (m & 2u) ? 0u : T_INF, (m & 4u) ? 0u : T_INF, (m & 8u) ? 0u : T_INF));
+      }
+      __syncthreads();
+    }
+  }
   if (r < 0 || r >= d.pix_rows()) return;
   {  // the image row re-encoded for the flood: 255 = never floods (border, above the last level, padding)
     const int ppitch = d.pix_pitch();
@@ -233,13 +263,10 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(FloodBuffers b, ImageDim
     }
   }
   if (r >= d.rows) return;
-  __syncthreads();  // the row of T is written: the seeds' zeros go on top of it
-  const uint32_t lo = b.row_start[(size_t)im * d.rows + r], hi = b.row_start[(size_t)im * d.rows + r + 1];
   const int ty = r / TILE_H;
   const uint32_t tile0 = (uint32_t)im * d.tiles_per_img() + (uint32_t)ty * d.tiles_x;
   for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
     const uint32_t c = __ldg(seeds_rc + 2 * (size_t)j + 1);
-    st_cg(Trow + c + T_PAD_L, 0u);
     // queue the tiles that must look at this seed (red-black order as in seed_init; the flood is a later launch)
     const int tx = (int)c / TILE_W;
     const uint32_t tile = tile0 + (uint32_t)tx;
@@ -300,46 +327,44 @@ __global__ void __launch_bounds__(256) seed_init_kernel(FloodBuffers b, ImageDim
                                                         const uint32_t* __restrict__ seed_off, uint32_t nseeds,
                                                         uint32_t colour_base) {
   if (ld_cg(&b.ctrl[FC_SEED_UNSORTED]) == 0u) return;  // sorted list: fill_rows_kernel has placed the seeds
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t tile = TILE_NONE_U, par = 0;
-  uint32_t r = 0, c = 0;
-  int ty = 0, tx = 0;
-  if (i < nseeds) {
-    int lo = 0, hi = d.n_img;  // slice of seed i: last b with seed_off[b] <= i
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(seed_off + mid) <= i) lo = mid; else hi = mid;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t n_pad = (nseeds + 31u) & ~31u;         // whole warps stay together for the match below
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+    uint32_t tile = TILE_NONE_U, par = 0;
+    uint32_t r = 0, c = 0;
+    int ty = 0, tx = 0;
+    if (i < nseeds) {
+      const int img = seed_slice_of(seed_off, d.n_img, i);
+      const uint2 rc = __ldg(reinterpret_cast<const uint2*>(seeds_rc) + i);
+      r = rc.x;
+      c = rc.y;
+      if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) {
+        atomicOr(&b.ctrl[FC_ERROR], 1u);
+      } else {
+        const uint32_t old = atomicExch(&b.T[(size_t)img * d.t_plane() + d.t_index((int)r, (int)c)], 0u);
+        st_cg(&b.lab[(size_t)img * d.px_per_img() + (size_t)r * d.cols + c],
+              LAB_RESOLVED | (colour_base + i - __ldg(seed_off + img) + 1u));
+        if (old == 0u) st_cg(&b.ctrl[FC_SEED_DUP], 1u);
+        ty = r / TILE_H;
+        tx = c / TILE_W;
+        tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
+        // Red-black order over the tiles: the even tiles (tx + ty even) start in bucket 0, the odd ones in
+        // bucket 1 -- they then already see their neighbours' results, a Gauss-Seidel step at tile level that
+        // saves re-activations.
+        par = (uint32_t)(tx + ty) & 1u;
+      }
     }
-    const int img = lo;
-    const uint2 rc = __ldg(reinterpret_cast<const uint2*>(seeds_rc) + i);
-    r = rc.x;
-    c = rc.y;
-    if (r >= (uint32_t)d.rows || c >= (uint32_t)d.cols) {
-      atomicOr(&b.ctrl[FC_ERROR], 1u);
-    } else {
-      const uint32_t old = atomicExch(&b.T[(size_t)img * d.t_plane() + d.t_index((int)r, (int)c)], 0u);
-      st_cg(&b.lab[(size_t)img * d.px_per_img() + (size_t)r * d.cols + c],
-            LAB_RESOLVED | (colour_base + i - __ldg(seed_off + img) + 1u));
-      if (old == 0u) st_cg(&b.ctrl[FC_SEED_DUP], 1u);
-      ty = r / TILE_H;
-      tx = c / TILE_W;
-      tile = (uint32_t)img * d.tiles_per_img() + ty * d.tiles_x + tx;
-      // Red-black order over the tiles: the even tiles (tx + ty even) start in bucket 0, the odd ones in
-      // bucket 1 -- they then already see their neighbours' results, a Gauss-Seidel step at tile level that
-      // saves re-activations.
-      par = (uint32_t)(tx + ty) & 1u;
+    // Lists from find_local_minima are row-major, so the 32 seeds of a warp share a handful of tiles: one lane
+    // per distinct tile queues it.  (the flood is a later launch: no fence needed here)
+    const uint32_t peers = __match_any_sync(0xffffffffu, tile);
+    if (tile != TILE_NONE_U) {
+      if ((int)(__ffs((int)peers) - 1) == (int)(threadIdx.x & 31)) push_tile<true>(b, tile, par);
+      // a seed on the tile's edge is in the halo of the neighbouring tile: that tile must look as well
+      if (r % TILE_H == 0 && ty > 0) push_tile<true>(b, tile - d.tiles_x, par ^ 1u);
+      if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile<true>(b, tile + d.tiles_x, par ^ 1u);
+      if (c % TILE_W == 0 && tx > 0) push_tile<true>(b, tile - 1, par ^ 1u);
+      if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile<true>(b, tile + 1, par ^ 1u);
     }
-  }
-  // Seeds arrive in row-major order (find_local_minima), so the 32 seeds of a warp share a handful of tiles:
-  // one lane per distinct tile queues it.  (the flood is a later launch: no fence needed here)
-  const uint32_t peers = __match_any_sync(0xffffffffu, tile);
-  if (tile != TILE_NONE_U) {
-    if ((int)(__ffs((int)peers) - 1) == (int)(threadIdx.x & 31)) push_tile<true>(b, tile, par);
-    // a seed on the tile's edge is in the halo of the neighbouring tile: that tile must look as well
-    if (r % TILE_H == 0 && ty > 0) push_tile<true>(b, tile - d.tiles_x, par ^ 1u);
-    if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile<true>(b, tile + d.tiles_x, par ^ 1u);
-    if (c % TILE_W == 0 && tx > 0) push_tile<true>(b, tile - 1, par ^ 1u);
-    if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile<true>(b, tile + 1, par ^ 1u);
   }
 }
 
@@ -366,11 +391,11 @@ __global__ void __launch_bounds__(256) seed_dup_kernel(FloodBuffers b, ImageDims
 cudaError_t launch_seed_init(FloodBuffers b, ImageDims d, const uint32_t* seeds_rc, const uint32_t* seed_off,
                              uint32_t nseeds, uint32_t colour_base, cudaStream_t s) {
   if (nseeds == 0) return cudaSuccess;
-  seed_init_kernel<<<(nseeds + 255) / 256, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds, colour_base);
+  const uint32_t want = (nseeds + 255) / 256, cap = (uint32_t)num_sms() * 32u;
+  seed_init_kernel<<<want < cap ? want : cap, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds, colour_base);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const uint32_t want = (nseeds + 255) / 256;
-  seed_dup_kernel<<<want < 4096u ? want : 4096u, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds, colour_base);
+  seed_dup_kernel<<<want < cap ? want : cap, 256, 0, s>>>(b, d, seeds_rc, seed_off, nseeds, colour_base);
   return cudaGetLastError();
 }
 

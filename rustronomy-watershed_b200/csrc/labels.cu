@@ -93,6 +93,10 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   // the row's first seed at or right of this warp's first column (rowbase, one entry per 32 columns), plus the
   // seeds to its left among the warp's 32 columns (a warp holds one row, 32 consecutive columns, per step).
   const bool sorted = __ldcg(&b.ctrl[FC_SEED_UNSORTED]) == 0u;
+  const int rb_pitch = 2 * d.tiles_x;
+  const uint32_t* rb_ptr = b.rowbase + ((size_t)img * d.rows + r0 + g * ROWS_PER_THREAD) * rb_pitch + 2 * tx + (lc >> 5);
+  const uint32_t col_first = b.colour_base + 1u - __ldg(b.seed_off + img);   // colour of the slice's seed 0, minus its index
+  const int halo_a = d.halo_top ? 0 : -1, halo_b = d.halo_bottom ? d.rows - 1 : -1;   // this plan's halo rows
   int nseed_px = 0;  // owned pixels that hold a seed (arrival time 0): the colours present on the canvas
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
@@ -103,11 +107,12 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
     const uint32_t* t = sm.T + (lr + 1) * LT_W + lc + LT_C0;
     const uint32_t tv = t[0];
     const bool inside = r < d.rows && c < d.cols;
-    const uint32_t seeds_here = __ballot_sync(0xffffffffu, inside && tv == 0u && !d.is_halo_row(r));
+    const bool halo = r == halo_a || r == halo_b;
+    const uint32_t seeds_here = __ballot_sync(0xffffffffu, inside && tv == 0u && !halo);
     if (inside) {
       const size_t p = base + (size_t)r * d.cols + c;
       b.lvl[p] = (tv >= T_INF) ? (uint8_t)255 : (uint8_t)(tv >> 24);
-      if (d.is_halo_row(r)) {
+      if (halo) {
         // a neighbouring strip owns this pixel: its slot behind the rim entries holds its own index ("pending")
         // until that strip's colour is imported; a pixel that is never coloured is resolved (UNCOLOURED) at once
         const uint32_t slot = rim_total + (r == 0 ? 0u : (uint32_t)d.cols) + (uint32_t)c;
@@ -118,8 +123,7 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
       } else if (tv == 0u) {
         if (sorted) {
           const uint32_t left = (uint32_t)__popc(seeds_here & ((1u << (lc & 31)) - 1u));
-          const uint32_t idx = __ldg(b.rowbase + ((size_t)img * d.rows + r) * (2 * d.tiles_x) + 2 * tx + (lc >> 5)) + left;
-          term = LAB_RESOLVED | (b.colour_base + idx - __ldg(b.seed_off + img) + 1u);
+          term = LAB_RESOLVED | (col_first + __ldg(rb_ptr + i * rb_pitch) + left);
         } else {
           term = __ldcg(b.lab + p);  // seed: coloured by seed_init
         }

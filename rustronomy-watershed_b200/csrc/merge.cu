@@ -52,7 +52,7 @@ struct MergeSmem {
     uint32_t edge[MR_HASH];      // afterwards: 8 warp-private segments of live edges, compacted every round
   } a;
   union {
-    struct { uint16_t lid[MR_NODES]; uint8_t lvl[MR_NODES + 3]; } n;  // until the edge list is built
+    struct { uint32_t node[MR_NODES]; } n;  // until the edge list is built: dense id | level << 16 of every node
     struct {
       uint32_t best[MR_NODES];   // root: smallest (level << 16 | slot) offered this round; after the id went
                                  // under another component: the edge it went along (an edge word)
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
         L[k] = __ldg(lab + p) & LAB_MASK;
         v = __ldg(lvl + p);
       }
-      sm.b.n.lvl[i] = (uint8_t)v;
+      sm.b.n.node[i] = v << 16;
       sm.open_[i] = 0;
       sm.parent[i] = (uint16_t)i;
       if (L[k] != 0u && sm.first == 0u) sm.first = L[k];  // any coloured label (benign race)
@@ -182,30 +182,41 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
           (d.halo_top && gr <= 1) || (d.halo_bottom && gr == d.rows - 1))
         sm.open_[id] = 1;
     }
-    sm.b.n.lid[i] = (uint16_t)id;
+    sm.b.n.node[i] |= id;  // (MR_NOLAB = 0xFFFF for uncoloured nodes)
   }
   __syncthreads();  // last use of the table: its memory becomes the edge list
 
-  // (c) the edges of my 8 pixels, compacted into my warp's segment of the edge list
+  // (c) the edges of my 8 pixels, compacted into my warp's segment of the edge list.  A tile whose nodes are all
+  // window centres of an unstriped image (every tile but those on the image's border) needs none of the
+  // per-pixel geometry tests.
   const int lc = tid % TILE_W, g = tid / TILE_W;
   uint32_t* seg = sm.a.edge + warp * MR_SEG;
   uint32_t cnt = 0;  // live edges in the segment (uniform across the warp)
+  const bool interior = !d.halo_top && !d.halo_bottom && d.row_offset == 0 && r0 >= 1 && c0 >= 1 &&
+                        r0 + TILE_H <= d.rows - 2 && c0 + TILE_W <= d.cols - 2;
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     const int r = g * ROWS_PER_THREAD + i;
     const int n = r * MR_NW + lc;
-    const int gr = r0 + r, gc = c0 + lc;
-    const uint32_t a = sm.b.n.lid[n];
-    const uint32_t br = sm.b.n.lid[n + 1], bd = sm.b.n.lid[n + MR_NW];
+    const uint32_t na = sm.b.n.node[n], nr = sm.b.n.node[n + 1], nd = sm.b.n.node[n + MR_NW];
+    const uint32_t a = na & 0xFFFFu, br = nr & 0xFFFFu, bd = nd & 0xFFFFu;
     uint32_t er = MR_NONE, ed = MR_NONE;
-    // An edge belongs to the strip that owns its upper / left pixel; a halo row's own edges are the
-    // neighbouring strip's.  Plain plans own every row.
-    if (a != MR_NOLAB && gr < d.rows && !(d.halo_top && gr == 0) && !(d.halo_bottom && gr == d.rows - 1)) {
-      const bool pin = d.is_centre(gr, gc);
-      if (br != MR_NOLAB && br != a && (pin || d.is_centre(gr, gc + 1)))
-        er = a | (br << 12) | (max((uint32_t)sm.b.n.lvl[n], (uint32_t)sm.b.n.lvl[n + 1]) << 24);
-      if (bd != MR_NOLAB && bd != a && (pin || d.is_centre(gr + 1, gc)))
-        ed = a | (bd << 12) | (max((uint32_t)sm.b.n.lvl[n], (uint32_t)sm.b.n.lvl[n + MR_NW]) << 24);
+    if (interior) {
+      if (a != MR_NOLAB) {
+        if (br != MR_NOLAB && br != a) er = a | (br << 12) | (max(na >> 16, nr >> 16) << 24);
+        if (bd != MR_NOLAB && bd != a) ed = a | (bd << 12) | (max(na >> 16, nd >> 16) << 24);
+      }
+    } else {
+      const int gr = r0 + r, gc = c0 + lc;
+      // An edge belongs to the strip that owns its upper / left pixel; a halo row's own edges are the
+      // neighbouring strip's.  Plain plans own every row.
+      if (a != MR_NOLAB && gr < d.rows && !(d.halo_top && gr == 0) && !(d.halo_bottom && gr == d.rows - 1)) {
+        const bool pin = d.is_centre(gr, gc);
+        if (br != MR_NOLAB && br != a && (pin || d.is_centre(gr, gc + 1)))
+          er = a | (br << 12) | (max(na >> 16, nr >> 16) << 24);
+        if (bd != MR_NOLAB && bd != a && (pin || d.is_centre(gr + 1, gc)))
+          ed = a | (bd << 12) | (max(na >> 16, nd >> 16) << 24);
+      }
     }
     // (no write of this loop can hit the table's last readers: they are behind the barrier above)
     uint32_t m = __ballot_sync(0xffffffffu, er != MR_NONE);
