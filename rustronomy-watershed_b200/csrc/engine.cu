@@ -344,6 +344,7 @@ extern "C" ws_status ws_plan_create(ws_ctx* ctx, size_t n_img, size_t rows, size
   alloc((void**)&p->mb.level_hist, 257 * 4);
   alloc((void**)&p->mb.level_cursor, 256 * 4);
   alloc((void**)&p->mb.red_count, 64);
+  alloc((void**)&p->mb.ovf_list, ntiles * 4);
   alloc((void**)&p->lvl_hist, n_img * 256 * 4);
   alloc((void**)&p->d_strip_off, 16);
   alloc((void**)&p->mb.unions, n_img * 256 * 4);
@@ -395,6 +396,7 @@ extern "C" void ws_plan_destroy(ws_plan* p) {
   cudaFree(p->mb.red_ab);
   cudaFree(p->mb.red_w);
   cudaFree(p->mb.red_count);
+  cudaFree(p->mb.ovf_list);
   cudaFree(p->mb.parent);
   cudaFree(p->mb.hook_to);
   cudaFree(p->mb.hook_lvl);
@@ -535,7 +537,7 @@ static ws_status plan_merge(ws_plan* p) {
   WS_TRY(plan_edge_buffers(p));
   // Per tile: FINAL forest edges (only counted) and DEFERRED edges between basins that reach the tile's rim.
   WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->seed_off, 1, p->mb.red_ab, p->mb.red_w,
-                                   p->mb.red_count, s));
+                                   p->mb.red_count, p->mb.ovf_list, s));
   WS_CUDA(ctx, cudaEventRecord(p->kev[7], s));
   p->kev_valid[6] = true;
 #ifdef WS_MERGE_STATS
@@ -1008,7 +1010,7 @@ extern "C" ws_status ws_plan_strip_forest(ws_plan* p, size_t ncolours_total, voi
   WS_TRY(plan_forest_buffers(p, ncolours_total, cap));
   // labels are GLOBAL colours here (colour_base + i + 1), so the colour id is label - 1: offsets {0, ...}
   WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, 1, p->mb.red_ab, p->mb.red_w,
-                                   p->mb.red_count, s));
+                                   p->mb.red_count, p->mb.ovf_list, s));
   WS_CUDA(ctx, launch_count_present(p->fb.lab, p->d, p->seeds, (uint32_t)p->nseeds, p->colour_base, p->mb.ndistinct, s));
   WS_CUDA(ctx, launch_forest_init(p->fo, (uint32_t)ncolours_total, 1, 1, ctx->sms, s));
   // open = the basins other strips may hold edges of: those on the halo rows, and on the first owned row below a
@@ -1058,7 +1060,7 @@ extern "C" ws_status ws_plan_strip_edges(ws_plan* p, const void** d_ab, const vo
   WS_TRY(plan_edge_buffers(p));
   // labels are GLOBAL colours here (colour_base + i + 1), so the colour id is label - 1: offsets {0, ...}
   WS_CUDA(ctx, launch_merge_reduce(p->fb.lab, p->fb.lvl, p->d, p->d_strip_off, 1, p->mb.red_ab, p->mb.red_w,
-                                   p->mb.red_count, s));
+                                   p->mb.red_count, p->mb.ovf_list, s));
   WS_CUDA(ctx, launch_count_present(p->fb.lab, p->d, p->seeds, (uint32_t)p->nseeds, p->colour_base, p->mb.ndistinct, s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS, p->mb.red_count, 4, cudaMemcpyDeviceToHost, s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl + FC_WORDS + 1, p->mb.ndistinct, 4, cudaMemcpyDeviceToHost, s));

@@ -119,7 +119,8 @@ struct MergeBuffers {
   uint32_t* level_cursor; // [256]
   uint2* red_ab;          // [cap] forest edges of the tiles (global colour ids), unsorted
   uint8_t* red_w;         // [cap] their levels
-  uint32_t* red_count;    // [1]
+  uint32_t* red_count;    // [16]: [0] edges emitted, [12] tiles on ovf_list, the rest statistics
+  uint32_t* ovf_list;     // [tiles_total] tiles that did not fit merge_reduce's small size
   uint2* edges;           // [cap] the same edges bucketed by level
   uint32_t* parent;       // [nseeds] union-find with path halving
   uint32_t* hook_to;      // [nseeds] immutable link written once when a root is hooked
@@ -132,8 +133,10 @@ struct MergeBuffers {
 // per-tile contraction + spanning-forest reduction in shared memory (merge.cu).  Edges: .x / .y = global
 // colour ids, bit 31 of .y = FINAL (a certain forest edge, only to be counted).  contract = 0: no FINAL edges.
 size_t merge_reduce_capacity(const ImageDims& d);
+// ovf_list [tiles_total]: scratch for the tiles that need the full-size kernel
 cudaError_t launch_merge_reduce(const uint32_t* lab, const uint8_t* lvl, ImageDims d, const uint32_t* seed_off,
-                                int contract, uint2* red_ab, uint8_t* red_w, uint32_t* red_count, cudaStream_t s);
+                                int contract, uint2* red_ab, uint8_t* red_w, uint32_t* red_count, uint32_t* ovf_list,
+                                cudaStream_t s);
 // counting sort by level: level_hist[0..256] = exclusive offsets, edges = buckets.  all = 0: only DEFERRED
 // edges are bucketed, FINAL ones are counted into fin_hist[slice][level]; all = 1: every edge is bucketed.
 cudaError_t launch_red_sort(const uint2* red_ab, const uint8_t* red_w, const uint32_t* red_count, int all,

@@ -35,55 +35,62 @@ constexpr int MR_NODES = MR_NW * MR_NH;        // 2145
 constexpr int MR_THREADS = 256;
 constexpr int MR_WARPS = MR_THREADS / 32;
 constexpr int MR_PER_THREAD = (MR_NODES + MR_THREADS - 1) / MR_THREADS;  // 9
-constexpr int MR_HASH = 4096;                  // label -> dense id table (load factor <= 0.53)
-constexpr int MR_SEG = 2 * 32 * ROWS_PER_THREAD;  // 512 edge slots per warp: 32 lanes x 8 pixels x (right, down)
 constexpr uint32_t MR_NONE = 0xFFFFFFFFu;
 constexpr uint16_t MR_NOLAB = 0xFFFFu;
-static_assert(MR_WARPS * MR_SEG == MR_HASH, "the edge list reuses the id table's memory");
 
-// Shared memory of one tile, 48.6 KB (4 CTAs per SM).  An edge is one word: id(a) | id(b) << 12 | level << 24.
+// Two sizes of the same kernel.  A tile can hold up to 2145 basins and 4096 edges, a real one holds a few hundred
+// (noise field: 260 basins, 1600 edges): the SMALL size -- up to 1024 basins, 384 edges per warp -- needs 28 KB
+// of shared memory and 40 registers, so six CTAs share an SM instead of four (the kernel is bound by the latency
+// of dependent shared-memory accesses: more warps is what it wants).  A tile that does not fit is put on a list
+// and redone by the FULL size, which fits everything.
+struct MrSmall { static constexpr int MAXN = 1024, HASH = 2048, HSHIFT = 21, SEG = 384; };
+struct MrFull  { static constexpr int MAXN = MR_NODES, HASH = 4096, HSHIFT = 20, SEG = 2 * 32 * ROWS_PER_THREAD; };
+
+// Shared memory of one tile.  An edge is one word: id(a) | id(b) << 12 | level << 24.
+template <typename Z>
 struct MergeSmem {
-  uint32_t label_of[MR_NODES];   // dense id -> colour
-  uint16_t parent[MR_NODES];     // union-find over dense ids; only a root's own thread re-parents it
-  uint8_t open_[MR_NODES + 3];   // dense id: the basin has pixels on the tile's rim; propagated to the roots
+  uint32_t label_of[Z::MAXN];    // dense id -> colour
+  uint16_t parent[Z::MAXN];      // union-find over dense ids; only a root's own thread re-parents it
+  uint8_t open_[(Z::MAXN + 3) & ~3];  // dense id: the basin has pixels on the tile's rim; propagated to the roots
                                  // (only ever set, so plain byte stores of 1 are race-free)
   union {
-    uint32_t table[MR_HASH];     // while dense ids are handed out: 0 = free, else the label / the id
-    uint32_t edge[MR_HASH];      // afterwards: 8 warp-private segments of live edges, compacted every round
+    uint32_t table[Z::HASH];     // while dense ids are handed out: 0 = free, else the label / the id
+    uint32_t edge[MR_WARPS * Z::SEG];  // afterwards: 8 warp-private segments of live edges, compacted every round
   } a;
   union {
     struct { uint32_t node[MR_NODES]; } n;  // until the edge list is built: dense id | level << 16 of every node
     struct {
-      uint32_t best[MR_NODES];   // root: smallest (level << 16 | slot) offered this round; after the id went
+      uint32_t best[Z::MAXN];    // root: smallest (level << 16 | slot) offered this round; after the id went
                                  // under another component: the edge it went along (an edge word)
-      uint16_t comp[MR_NODES];   // root of every id at the start of the round
-      uint16_t link[MR_NODES];   // FINAL moves only: the basin at the far end of the edge (else the id itself);
+      uint16_t comp[Z::MAXN];    // root of every id at the start of the round
+      uint16_t link[Z::MAXN];    // FINAL moves only: the basin at the far end of the edge (else the id itself);
                                  // following the links gives the identity of a contracted basin; bit 15: FINAL
     } r;
   } b;
-  uint32_t nlab, nout, gpos, first;
+  uint32_t nlab, nout, gpos, first, overflow;
 };
 
 // One Boruvka over the tile's basin graph; every component picks its lightest edge in every round.  A pick
 // made by a component that holds closed basins only is FINAL (cut property: all edges of a closed basin lie
 // in this tile), every other pick is DEFERRED.  `contract` = 0 treats every basin as open (no FINAL edges).
-__global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t* __restrict__ lab,
-                                                                  const uint8_t* __restrict__ lvl, ImageDims d,
-                                                                  const uint32_t* __restrict__ seed_off, int contract,
-                                                                  uint2* __restrict__ red_ab, uint8_t* __restrict__ red_w,
-                                                                  uint32_t* __restrict__ red_count) {
-  __shared__ MergeSmem sm;
+// Returns false when the tile does not fit this size (nothing has been emitted then).
+template <typename Z>
+__device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, const uint32_t* __restrict__ lab,
+                                           const uint8_t* __restrict__ lvl, const ImageDims& d,
+                                           const uint32_t* __restrict__ seed_off, const int contract,
+                                           uint2* __restrict__ red_ab, uint8_t* __restrict__ red_w,
+                                           uint32_t* __restrict__ red_count) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tpi = d.tiles_per_img();
-  const int img = blockIdx.x / tpi;
-  const int trem = blockIdx.x - img * tpi;
+  const int img = tile / tpi;
+  const int trem = tile - img * tpi;
   const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
   const int r0 = ty * TILE_H, c0 = tx * TILE_W;
   const size_t base = (size_t)img * d.px_per_img();
 
   // (a) labels and levels of the tile and of its right / bottom neighbours
   uint32_t L[MR_PER_THREAD];
-  if (tid == 0) { sm.nlab = 0; sm.nout = 0; sm.first = 0; }
+  if (tid == 0) { sm.nlab = 0; sm.nout = 0; sm.first = 0; sm.overflow = 0; }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < MR_PER_THREAD; ++k) {
@@ -99,19 +106,21 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
         v = __ldg(lvl + p);
       }
       sm.b.n.node[i] = v << 16;
-      sm.open_[i] = 0;
-      sm.parent[i] = (uint16_t)i;
       if (L[k] != 0u && sm.first == 0u) sm.first = L[k];  // any coloured label (benign race)
     }
   }
-  for (int i = tid; i < MR_HASH; i += MR_THREADS) sm.a.table[i] = 0u;
+  for (int i = tid; i < Z::MAXN; i += MR_THREADS) {
+    sm.open_[i] = 0;
+    sm.parent[i] = (uint16_t)i;
+  }
+  for (int i = tid; i < Z::HASH; i += MR_THREADS) sm.a.table[i] = 0u;
   __syncthreads();
   {  // a tile inside one basin (most tiles of a smooth field) has no edge at all
     const uint32_t f = sm.first;
     bool differs = false;
 #pragma unroll
     for (int k = 0; k < MR_PER_THREAD; ++k) differs |= (L[k] != 0u && L[k] != f);
-    if (!__syncthreads_or(differs)) return;
+    if (!__syncthreads_or(differs)) return true;
   }
 
   // (b) dense ids, one per distinct label: insert the labels into an open-addressing table, number the
@@ -125,13 +134,18 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     const uint32_t prev = __shfl_up_sync(0xffffffffu, l, 1);
     const bool lead = lane == 0 || prev != l;
     const uint32_t leaders = __ballot_sync(0xffffffffu, lead);
-    uint32_t h = (l * 2654435761u) >> 20;
+    uint32_t h = (l * 2654435761u) >> Z::HSHIFT;
     if (lead && l != 0u) {
-      for (;;) {
+      int probes = 0;
+      for (;; ++probes) {
+        if (probes == Z::HASH) {   // more distinct labels than slots (small size only)
+          sm.overflow = 1;
+          break;
+        }
         uint32_t cur = ((volatile uint32_t*)sm.a.table)[h];
         if (cur == 0u) cur = atomicCAS(&sm.a.table[h], 0u, l);
         if (cur == 0u || cur == l) break;
-        h = (h + 1u) & (MR_HASH - 1);
+        h = (h + 1u) & (Z::HASH - 1);
       }
     }
     const int src = 31 - __clz((int)(leaders & (0xFFFFFFFFu >> (31 - lane))));  // my run's first lane
@@ -139,13 +153,13 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
   }
   __syncthreads();
   {
-    uint32_t key[MR_HASH / MR_THREADS];
+    uint32_t key[Z::HASH / MR_THREADS];
 #pragma unroll
-    for (int k = 0; k < MR_HASH / MR_THREADS; ++k) key[k] = sm.a.table[tid + k * MR_THREADS];
+    for (int k = 0; k < Z::HASH / MR_THREADS; ++k) key[k] = sm.a.table[tid + k * MR_THREADS];
     // ids in blocks: one shared atomic per warp
     uint32_t mine = 0;
 #pragma unroll
-    for (int k = 0; k < MR_HASH / MR_THREADS; ++k) mine += (key[k] != 0u);
+    for (int k = 0; k < Z::HASH / MR_THREADS; ++k) mine += (key[k] != 0u);
     uint32_t incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -157,15 +171,16 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     wbase = __shfl_sync(0xffffffffu, wbase, 31);
     uint32_t id = wbase + incl - mine;
 #pragma unroll
-    for (int k = 0; k < MR_HASH / MR_THREADS; ++k) {
+    for (int k = 0; k < Z::HASH / MR_THREADS; ++k) {
       if (key[k] == 0u) continue;
-      sm.label_of[id] = key[k];
+      if (id < (uint32_t)Z::MAXN) sm.label_of[id] = key[k];
       sm.a.table[tid + k * MR_THREADS] = id;  // (only this thread touches the slot in this phase)
       ++id;
     }
   }
   __syncthreads();
   const int nlab = (int)sm.nlab;
+  if (nlab > Z::MAXN || sm.overflow) return false;   // (uniform: both were written before the barrier)
 #pragma unroll
   for (int k = 0; k < MR_PER_THREAD; ++k) {
     const int i = tid + k * MR_THREADS;
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
   // window centres of an unstriped image (every tile but those on the image's border) needs none of the
   // per-pixel geometry tests.
   const int lc = tid % TILE_W, g = tid / TILE_W;
-  uint32_t* seg = sm.a.edge + warp * MR_SEG;
+  uint32_t* seg = sm.a.edge + warp * Z::SEG;
   uint32_t cnt = 0;  // live edges in the segment (uniform across the warp)
   const bool interior = !d.halo_top && !d.halo_bottom && d.row_offset == 0 && r0 >= 1 && c0 >= 1 &&
                         r0 + TILE_H <= d.rows - 2 && c0 + TILE_W <= d.cols - 2;
@@ -220,14 +235,18 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     }
     // (no write of this loop can hit the table's last readers: they are behind the barrier above)
     uint32_t m = __ballot_sync(0xffffffffu, er != MR_NONE);
-    if (er != MR_NONE) seg[cnt + __popc(m & ((1u << lane) - 1u))] = er;
+    uint32_t pos = cnt + __popc(m & ((1u << lane) - 1u));
+    if (er != MR_NONE && pos < (uint32_t)Z::SEG) seg[pos] = er;
     cnt += __popc(m);
     m = __ballot_sync(0xffffffffu, ed != MR_NONE);
-    if (ed != MR_NONE) seg[cnt + __popc(m & ((1u << lane) - 1u))] = ed;
+    pos = cnt + __popc(m & ((1u << lane) - 1u));
+    if (ed != MR_NONE && pos < (uint32_t)Z::SEG) seg[pos] = ed;
     cnt += __popc(m);
   }
-  if (!__syncthreads_or(cnt != 0u)) return;  // no edge between different basins in this tile
-  // (lid / lvl are dead from here on: their memory becomes best / comp / link)
+  if (cnt > (uint32_t)Z::SEG) sm.overflow = 1;   // more edges than this size holds (small size only)
+  if (!__syncthreads_or(cnt != 0u)) return true;  // no edge between different basins in this tile
+  if (sm.overflow) return false;                  // (written before the barrier: uniform)
+  // (node[] is dead from here on: its memory becomes best / comp / link)
   for (int i = tid; i < nlab; i += MR_THREADS) {
     sm.b.r.best[i] = MR_NONE;
     sm.b.r.comp[i] = (uint16_t)i;
@@ -243,7 +262,7 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
   // Round 1: every basin is its own component and every edge is alive -- offers only.
   for (uint32_t j = lane; j < cnt; j += 32) {
     const uint32_t e = seg[j];
-    const uint32_t key = ((e >> 24) << 16) | (uint32_t)(warp * MR_SEG + j);
+    const uint32_t key = ((e >> 24) << 16) | (uint32_t)(warp * Z::SEG + j);
     atomicMin(&sm.b.r.best[e & 0xFFFu], key);
     atomicMin(&sm.b.r.best[(e >> 12) & 0xFFFu], key);
   }
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
       if (alive) {
         const uint32_t pos = kept + __popc(m & ((1u << lane) - 1u));
         seg[pos] = e;
-        const uint32_t key = ((e >> 24) << 16) | (uint32_t)(warp * MR_SEG + pos);
+        const uint32_t key = ((e >> 24) << 16) | (uint32_t)(warp * Z::SEG + pos);
         atomicMin(&sm.b.r.best[cu], key);
         atomicMin(&sm.b.r.best[cv], key);
         any = true;
@@ -325,7 +344,7 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
 #ifdef WS_MERGE_STATS
   if (tid == 0) { atomicAdd(&red_count[8], 1u); atomicAdd(&red_count[9], (uint32_t)nlab); atomicAdd(&red_count[10], nout); }
 #endif
-  if (nout == 0u) return;
+  if (nout == 0u) return true;
   if (tid == 0) sm.gpos = atomicAdd(red_count, nout);
   __syncthreads();
   const uint32_t gbase = __ldg(seed_off + img) - 1u;  // global colour id = seed_off[img] + colour - 1
@@ -345,15 +364,51 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_kernel(const uint32_t
     red_w[at] = (uint8_t)(e >> 24);
     ++at;
   }
+  return true;
+}
+
+// every tile with the small size; the ones that do not fit go on ovf_list (ovf_count = red_count[12])
+__global__ void __launch_bounds__(MR_THREADS, 6) merge_reduce_kernel(const uint32_t* __restrict__ lab,
+                                                                     const uint8_t* __restrict__ lvl, ImageDims d,
+                                                                     const uint32_t* __restrict__ seed_off, int contract,
+                                                                     uint2* __restrict__ red_ab, uint8_t* __restrict__ red_w,
+                                                                     uint32_t* __restrict__ red_count,
+                                                                     uint32_t* __restrict__ ovf_list) {
+  __shared__ MergeSmem<MrSmall> sm;
+  if (!merge_tile<MrSmall>(sm, (int)blockIdx.x, lab, lvl, d, seed_off, contract, red_ab, red_w, red_count) &&
+      threadIdx.x == 0)
+    ovf_list[atomicAdd(&red_count[12], 1u)] = blockIdx.x;
+}
+
+// the listed tiles with the full size (a persistent grid: the list is usually empty)
+__global__ void __launch_bounds__(MR_THREADS) merge_reduce_full_kernel(const uint32_t* __restrict__ lab,
+                                                                       const uint8_t* __restrict__ lvl, ImageDims d,
+                                                                       const uint32_t* __restrict__ seed_off, int contract,
+                                                                       uint2* __restrict__ red_ab, uint8_t* __restrict__ red_w,
+                                                                       uint32_t* __restrict__ red_count,
+                                                                       const uint32_t* __restrict__ ovf_list) {
+  __shared__ MergeSmem<MrFull> sm;
+  const uint32_t n = red_count[12];
+  for (uint32_t k = blockIdx.x; k < n; k += gridDim.x) {
+    merge_tile<MrFull>(sm, (int)ovf_list[k], lab, lvl, d, seed_off, contract, red_ab, red_w, red_count);
+    __syncthreads();  // the next tile reuses the shared memory
+  }
 }
 
 size_t merge_reduce_capacity(const ImageDims& d) { return (size_t)d.tiles_total() * (MR_NODES - 1); }
 
 cudaError_t launch_merge_reduce(const uint32_t* lab, const uint8_t* lvl, ImageDims d, const uint32_t* seed_off,
-                                int contract, uint2* red_ab, uint8_t* red_w, uint32_t* red_count, cudaStream_t s) {
+                                int contract, uint2* red_ab, uint8_t* red_w, uint32_t* red_count, uint32_t* ovf_list,
+                                cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(red_count, 0, 16 * sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  merge_reduce_kernel<<<d.tiles_total(), MR_THREADS, 0, s>>>(lab, lvl, d, seed_off, contract, red_ab, red_w, red_count);
+  merge_reduce_kernel<<<d.tiles_total(), MR_THREADS, 0, s>>>(lab, lvl, d, seed_off, contract, red_ab, red_w, red_count,
+                                                               ovf_list);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int want = d.tiles_total(), cap = num_sms() * 4;
+  merge_reduce_full_kernel<<<want < cap ? want : cap, MR_THREADS, 0, s>>>(lab, lvl, d, seed_off, contract, red_ab, red_w,
+                                                                             red_count, ovf_list);
   return cudaGetLastError();
 }
 

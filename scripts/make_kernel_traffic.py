@@ -13,7 +13,7 @@ import re
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-NAMES = {"fill_state_kernel": "fill_state", "seed_init_kernel": "seed_init", "flood_kernel": "flood",
+NAMES = {"fill_state_kernel": "fill_state", "fill_rows_kernel": "fill_state", "seeds_scan_kernel": "seeds_scan", "seed_init_kernel": "seed_init", "flood_kernel": "flood",
          "label_tile_kernel": "label_tile", "rim_jump_kernel": "rim_jump", "label_finish_kernel": "label_finish",
          "merge_reduce_kernel": "merge_reduce", "forest_init_kernel": "forest_init",
          "forest_boruvka_kernel": "forest_boruvka"}
