@@ -201,43 +201,102 @@ __global__ void __launch_bounds__(256) seeds_scan_empty_kernel(FloodBuffers b, I
   for (int r = threadIdx.x; r < d.rows; r += blockDim.x) b.row_start[(size_t)img * d.rows + r] = first;
 }
 
-// one CTA per row of the padded arrival-time plane
+// One CTA per row of the padded arrival-time plane.  Everything the row needs comes from a bitmap of its seeds'
+// columns in shared memory: the words of T (written once: INF, or 0 under a set bit), rowbase (prefix popcounts
+// of the bitmap words: the index of the first seed at or right of every 32-column block), and the tiles to queue
+// (the two words of a tile are not both zero; a seed in a tile's first / last column or row also concerns the
+// neighbour).  Rows wider than FR_COLS columns take several passes.
 __global__ void __launch_bounds__(256) fill_rows_kernel(FloodBuffers b, ImageDims d, const uint8_t* __restrict__ img,
                                                         uint32_t lmax, const uint32_t* __restrict__ seeds_rc) {
   if (ld_cg(&b.ctrl[FC_SEED_UNSORTED]) != 0u) return;
+  constexpr int FR_COLS = 32768;                    // image columns per pass: 4 KB of bitmap
+  constexpr int FR_WORDS = FR_COLS / 32;
+  __shared__ uint32_t s_bits[FR_WORDS];
+  __shared__ uint32_t s_warp[8], s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t_rows = d.t_rows(), pitch = d.t_pitch();
   const int im = blockIdx.x / t_rows, prow = blockIdx.x - im * t_rows;
   const int r = prow - 1;  // image row of this padded row
-  uint32_t* Trow = b.T + (size_t)im * d.t_plane() + (size_t)prow * pitch;
+  uint4* T4 = reinterpret_cast<uint4*>(b.T + (size_t)im * d.t_plane() + (size_t)prow * pitch);
   const uint4 inf4 = make_uint4(T_INF, T_INF, T_INF, T_INF);
-  // Rows with seeds: a bitmap of the seeds' columns in shared memory, then every word of the row is written once
-  // (INF first and the zeros on top of it later made the lines travel twice: 1.1 GB read + 0.6 GB extra written).
-  constexpr int FR_COLS = 32768;                    // columns per pass: 4 KB of bitmap
-  __shared__ uint32_t s_bits[FR_COLS / 32];
   const bool image_row = r >= 0 && r < d.rows;
   uint32_t lo = 0, hi = 0;
   if (image_row) {
     lo = b.row_start[(size_t)im * d.rows + r];
     hi = b.row_start[(size_t)im * d.rows + r + 1];
   }
-  if (lo == hi) {
-    for (int i = threadIdx.x; i < pitch / 4; i += blockDim.x) __stcg(reinterpret_cast<uint4*>(Trow) + i, inf4);
+  const int wcols = d.tiles_x * TILE_W;             // image columns the plane has room for (uint4 1 .. wcols / 4)
+  if (tid == 0) {                                   // the pad words left and right of them
+    __stcg(T4, inf4);
+    __stcg(T4 + wcols / 4 + 1, inf4);
+  }
+  if (!image_row) {
+    for (int j = tid; j < wcols / 4; j += blockDim.x) __stcg(T4 + 1 + j, inf4);
   } else {
-    // padded column p holds image column p - T_PAD_L
-    for (int p0 = 0; p0 < pitch; p0 += FR_COLS) {
-      const int np = min(FR_COLS, pitch - p0);      // a multiple of 8
-      for (int i = threadIdx.x; i < (np + 31) / 32; i += blockDim.x) s_bits[i] = 0u;
+    const int ty = r / TILE_H;
+    const uint32_t tile0 = (uint32_t)im * d.tiles_per_img() + (uint32_t)ty * d.tiles_x;
+    uint32_t* rb = b.rowbase + ((size_t)im * d.rows + r) * (2 * d.tiles_x);
+    uint32_t passbase = lo;                         // seeds of the row left of this pass
+    for (int cb = 0; cb < wcols; cb += FR_COLS) {
+      const int np = min(FR_COLS, wcols - cb);      // a multiple of 64
+      const int nw = np / 32;
+      for (int i = tid; i < nw; i += blockDim.x) s_bits[i] = 0u;
       __syncthreads();
-      for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
-        const int p = (int)__ldg(seeds_rc + 2 * (size_t)j + 1) + T_PAD_L - p0;
-        if (p >= 0 && p < np) atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+      for (uint32_t j = lo + tid; j < hi; j += blockDim.x) {
+        const int c = (int)__ldg(seeds_rc + 2 * (size_t)j + 1) - cb;
+        if (c >= 0 && c < np) atomicOr(&s_bits[c >> 5], 1u << (c & 31));
       }
       __syncthreads();
-      for (int i = threadIdx.x; i < np / 4; i += blockDim.x) {
-        const uint32_t m = (s_bits[i >> 3] >> ((i & 7) * 4)) & 0xFu;
-        __stcg(reinterpret_cast<uint4*>(Trow + p0) + i,
-               make_uint4((m & 1u) ? 0u : T_INF, (m & 2u) ? 0u : T_INF, (m & 4u) ? 0u : T_INF, (m & 8u) ? 0u : T_INF));
+      // arrival times
+      for (int j = tid; j < np / 4; j += blockDim.x) {
+        const uint32_t m = (s_bits[j >> 3] >> ((j & 7) * 4)) & 0xFu;
+        __stcg(T4 + 1 + cb / 4 + j, m == 0u ? inf4
+                                             : make_uint4((m & 1u) ? 0u : T_INF, (m & 2u) ? 0u : T_INF,
+                                                          (m & 4u) ? 0u : T_INF, (m & 8u) ? 0u : T_INF));
       }
+      // rowbase: exclusive prefix popcount over the bitmap words (4 consecutive words per thread)
+      {
+        uint32_t w[4], mine = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = tid * 4 + k;
+          w[k] = i < nw ? (uint32_t)__popc(s_bits[i]) : 0u;
+          mine += w[k];
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+        for (int k = 0; k < warp; ++k) before += s_warp[k];
+        if (tid == 255) s_total = before + incl;
+        uint32_t run = passbase + before + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = tid * 4 + k;
+          if (i < nw) rb[cb / 32 + i] = run;
+          run += w[k];
+        }
+      }
+      // tiles to queue (red-black order as in seed_init; the flood is a later launch)
+      for (int t = tid; t < np / TILE_W; t += blockDim.x) {
+        const uint32_t w0 = s_bits[2 * t], w1 = s_bits[2 * t + 1];
+        if ((w0 | w1) == 0u) continue;
+        const int tx = cb / TILE_W + t;
+        const uint32_t tile = tile0 + (uint32_t)tx;
+        const uint32_t par = (uint32_t)(tx + ty) & 1u;
+        push_tile<true>(b, tile, par);
+        if (r % TILE_H == 0 && ty > 0) push_tile<true>(b, tile - d.tiles_x, par ^ 1u);
+        if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile<true>(b, tile + d.tiles_x, par ^ 1u);
+        if ((w0 & 1u) && tx > 0) push_tile<true>(b, tile - 1, par ^ 1u);
+        if ((w1 >> 31) && tx + 1 < d.tiles_x) push_tile<true>(b, tile + 1, par ^ 1u);
+      }
+      __syncthreads();
+      passbase += s_total;
       __syncthreads();
     }
   }
@@ -246,49 +305,27 @@ __global__ void __launch_bounds__(256) fill_rows_kernel(FloodBuffers b, ImageDim
     const int ppitch = d.pix_pitch();
     uchar4* P4 = reinterpret_cast<uchar4*>(b.pix + (size_t)im * d.pix_plane() + (size_t)r * ppitch);
     const bool inner = r >= 1 && r <= d.rows - 2;
-    const uint8_t* row = img + (size_t)im * d.px_per_img() + (size_t)r * d.cols;
-    for (int i = threadIdx.x; i < ppitch / 4; i += blockDim.x) {
+    const uint8_t* row = img + (size_t)im * d.px_per_img() + (size_t)(inner ? r : 0) * d.cols;
+    const bool words = inner && (d.cols & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 3u) == 0;
+    for (int i = tid; i < ppitch / 4; i += blockDim.x) {
       uint32_t v[4] = {255u, 255u, 255u, 255u};
       if (inner) {
+        if (words && 4 * i + 3 < d.cols) {
+          const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(row) + i);
+          v[0] = x & 0xFFu; v[1] = (x >> 8) & 0xFFu; v[2] = (x >> 16) & 0xFFu; v[3] = x >> 24;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (4 * i + k < d.cols) v[k] = __ldg(row + 4 * i + k);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int c = 4 * i + k;
-          if (c >= 1 && c <= d.cols - 2) {
-            const uint32_t x = __ldg(row + c);
-            v[k] = x > lmax ? 255u : x;
-          }
+          v[k] = (c >= 1 && c <= d.cols - 2 && v[k] <= lmax) ? v[k] : 255u;
         }
       }
       P4[i] = make_uchar4((unsigned char)v[0], (unsigned char)v[1], (unsigned char)v[2], (unsigned char)v[3]);
     }
-  }
-  if (r >= d.rows) return;
-  const int ty = r / TILE_H;
-  const uint32_t tile0 = (uint32_t)im * d.tiles_per_img() + (uint32_t)ty * d.tiles_x;
-  for (uint32_t j = lo + threadIdx.x; j < hi; j += blockDim.x) {
-    const uint32_t c = __ldg(seeds_rc + 2 * (size_t)j + 1);
-    // queue the tiles that must look at this seed (red-black order as in seed_init; the flood is a later launch)
-    const int tx = (int)c / TILE_W;
-    const uint32_t tile = tile0 + (uint32_t)tx;
-    const uint32_t par = (uint32_t)(tx + ty) & 1u;
-    const bool first_of_tile = j == lo || (int)__ldg(seeds_rc + 2 * (size_t)j - 1) / TILE_W != tx;
-    if (first_of_tile) {
-      push_tile<true>(b, tile, par);
-      if (r % TILE_H == 0 && ty > 0) push_tile<true>(b, tile - d.tiles_x, par ^ 1u);
-      if (r % TILE_H == TILE_H - 1 && ty + 1 < d.tiles_y) push_tile<true>(b, tile + d.tiles_x, par ^ 1u);
-    }
-    if (c % TILE_W == 0 && tx > 0) push_tile<true>(b, tile - 1, par ^ 1u);
-    if (c % TILE_W == TILE_W - 1 && tx + 1 < d.tiles_x) push_tile<true>(b, tile + 1, par ^ 1u);
-  }
-  // rowbase: index of the first seed of this row at or right of every 32-column block's first column
-  for (int t = threadIdx.x; t < 2 * d.tiles_x; t += blockDim.x) {
-    uint32_t a = lo, z = hi;
-    const uint32_t want = (uint32_t)t * (TILE_W / 2);
-    while (a < z) {
-      const uint32_t mid = (a + z) >> 1;
-      if (__ldg(seeds_rc + 2 * (size_t)mid + 1) < want) a = mid + 1; else z = mid;
-    }
-    b.rowbase[((size_t)im * d.rows + r) * (2 * d.tiles_x) + t] = a;
   }
 }
 
