@@ -644,7 +644,8 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   WS_CUDA(ctx, cudaEventRecord(p->kev[6], s));
   for (int i = 0; i < 6; ++i) p->kev_valid[i] = true;
   WS_CUDA(ctx, cudaEventRecord(p->ev[3], s));
-  p->stats[4] += 4 + (nseeds_total ? 1 : 0);
+  // seeds_scan_empty, fill_rows, fill_state, flood, label_tile, rim_jump, label_finish (+ seeds_scan, seed_init, seed_dup)
+  p->stats[4] += 7 + (nseeds_total ? 3 : 0);
   if (cfg->kind == WS_MERGING) WS_TRY(plan_merge(p));
   WS_CUDA(ctx, cudaEventRecord(p->ev[4], s));
   WS_CUDA(ctx, cudaMemcpyAsync(p->h_ctrl, p->fb.ctrl, FC_WORDS * 4, cudaMemcpyDeviceToHost, s));

@@ -518,9 +518,12 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
 
   // stage -> working tile (odd stride).  Staged row = image columns c0-4 .. c0+67; the working
   // tile keeps c0-1 .. c0+64.
-  for (int i = tid; i < SM_H * (TILE_W + 2); i += FLOOD_CONSUMERS) {
-    const int lr = i / (TILE_W + 2), lc = i - lr * (TILE_W + 2);
-    sm.W[lr * SM_W + lc] = st.T[lr * STG_W + lc + (T_PAD_L - 1)];
+  for (int lr = warp; lr < SM_H; lr += FLOOD_CONSUMERS / 32) {   // a warp per row: no index arithmetic per word
+    const uint32_t* src = st.T + lr * STG_W + (T_PAD_L - 1);
+    uint32_t* dst = sm.W + lr * SM_W;
+    dst[lane] = src[lane];
+    dst[lane + 32] = src[lane + 32];
+    if (lane < TILE_W + 2 - 64) dst[lane + 64] = src[lane + 64];
   }
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(st.pix);
