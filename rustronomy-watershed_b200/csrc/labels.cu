@@ -176,15 +176,32 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   __syncthreads();
   if (tid == 0 && sm.nseed_px) atomicAdd(&ndistinct[img], sm.nseed_px);  // one global atomic per tile
 
-  // pointer jumping inside the tile (reads and writes separated by barriers); `act` = my pixels that
-  // still hold an in-tile pointer
+  // Pointer jumping inside the tile; `act` = my pixels that still hold an in-tile pointer.  Rounds of doubling
+  // (reads and writes separated by barriers) while many threads have work: a round costs every thread its
+  // eight bit tests and two barriers whether or not it has anything left.  Once fewer than a quarter of the
+  // threads are active -- after two or three rounds on a noise field, whose chains are a few pixels long -- the
+  // rest is walked sequentially, without barriers: a word only ever changes from a pointer to the final word of
+  // its own chain, so whatever a racing reader sees is a valid successor or the end.
   uint32_t act = 0, cur[ROWS_PER_THREAD];
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     cur[i] = sm.w[(g * ROWS_PER_THREAD + i) * TILE_W + lc];
     if (lt_is_local(cur[i])) act |= 1u << i;
   }
-  while (__syncthreads_or(act != 0u)) {
+  for (;;) {
+    const int nact = __syncthreads_count(act != 0u);
+    if (nact == 0) break;
+    if (nact < LT_THREADS / 4) {
+#pragma unroll
+      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+        if (!(act & (1u << i))) continue;
+        uint32_t x = cur[i];
+        while (lt_is_local(x)) x = ((volatile uint32_t*)sm.w)[x & (TILE_H * TILE_W - 1)];
+        sm.w[(g * ROWS_PER_THREAD + i) * TILE_W + lc] = x;
+      }
+      __syncthreads();
+      break;
+    }
 #pragma unroll
     for (int i = 0; i < ROWS_PER_THREAD; ++i)
       if (act & (1u << i)) cur[i] = sm.w[cur[i] & (TILE_H * TILE_W - 1)];  // my successor's word: its successor, or the end
