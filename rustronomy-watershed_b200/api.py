@@ -19,6 +19,7 @@ from typing import Callable, Generic, List, Optional, Sequence, Tuple, TypeVar
 import numpy as np
 
 from . import _native as N
+from . import plotting
 
 T = TypeVar("T")
 
@@ -62,7 +63,7 @@ class HookCtx:
 
 
 class TransformBuilder(Generic[T]):
-    """lib.rs:908-1047 (the plotting options are out of scope)."""
+    """lib.rs:908-1047, including the `plots` feature's two options (lib.rs:972-994)."""
 
     def __init__(self):
         self.max_water_level = NORMAL_MAX          # lib.rs:942
@@ -71,6 +72,8 @@ class TransformBuilder(Generic[T]):
         self.device = 0
         self.tie_break = N.WS_TIE_FIRST
         self.tie_seed: Optional[int] = None
+        self.plot_path: Optional[str] = None       # lib.rs:939
+        self.plot_colour_map = None                # lib.rs:941; viridis when unset (lib.rs:1011)
 
     @classmethod
     def new(cls) -> "TransformBuilder":
@@ -92,6 +95,16 @@ class TransformBuilder(Generic[T]):
 
     def set_wlvl_hook(self, hook: Callable[[HookCtx], T]) -> "TransformBuilder":
         self.wlvl_hook = hook
+        return self
+
+    def set_plot_colour_map(self, colour_map) -> "TransformBuilder":
+        """lib.rs:975-985: `colour_map(count, min, max)`, vectorised (see plotting.py)."""
+        self.plot_colour_map = colour_map
+        return self
+
+    def set_plot_folder(self, path) -> "TransformBuilder":
+        """lib.rs:991-994: with a folder set every water level writes `ws_lvl{level}.png` there."""
+        self.plot_path = str(path)
         return self
 
     def set_device(self, device: int) -> "TransformBuilder":
@@ -119,12 +132,12 @@ class TransformBuilder(Generic[T]):
     def build_merging(self) -> "MergingWatershed":
         self._validate(N.WS_MERGING)
         return MergingWatershed(self.max_water_level, self.edge_correction, self.wlvl_hook, self.device,
-                                self.tie_break, self.tie_seed)
+                                self.tie_break, self.tie_seed, self.plot_path, self.plot_colour_map)
 
     def build_segmenting(self) -> "SegmentingWatershed":
         self._validate(N.WS_SEGMENTING)
         return SegmentingWatershed(self.max_water_level, self.edge_correction, self.wlvl_hook, self.device,
-                                   self.tie_break, self.tie_seed)
+                                   self.tie_break, self.tie_seed, self.plot_path, self.plot_colour_map)
 
 
 class WatershedUtils:
@@ -182,7 +195,10 @@ class Watershed(WatershedUtils, Generic[T]):
 
     def __init__(self, max_water_level: int, edge_correction: bool,
                  wlvl_hook: Optional[Callable[[HookCtx], T]], device: int = 0,
-                 tie_break: int = N.WS_TIE_FIRST, tie_seed: Optional[int] = None):
+                 tie_break: int = N.WS_TIE_FIRST, tie_seed: Optional[int] = None,
+                 plot_path: Optional[str] = None, plot_colour_map=None):
+        self.plot_path = plot_path
+        self.plot_colour_map = plot_colour_map if plot_colour_map is not None else plotting.viridis  # lib.rs:1011
         self.max_water_level = max_water_level
         self.edge_correction = edge_correction
         self.wlvl_hook = wlvl_hook
@@ -207,6 +223,7 @@ class Watershed(WatershedUtils, Generic[T]):
     # -- Watershed::transform --------------------------------------------------
     def transform(self, input: np.ndarray, seeds: Sequence, out: Optional[np.ndarray] = None) -> np.ndarray:
         """`out` (extension): a caller-owned C-order uint64 array to fill, e.g. pinned memory."""
+        self._plot_pass(input, seeds)
         ctx = self._ctx()
         cfg, view, s = self._cfg(), N.image_view(input), N.seeds_array(seeds)
         shape = tuple(input.shape) if self.KIND == N.WS_MERGING else self._out_shape(input)
@@ -219,10 +236,29 @@ class Watershed(WatershedUtils, Generic[T]):
         return out
 
     # -- Watershed::transform_with_hook ----------------------------------------
+    def _plot_level(self, water_level: int, colours: np.ndarray) -> None:
+        """lib.rs:1472-1487 / 1758-1773: the level's label image without the edge-correction padding; a plot
+        that fails is reported and the transform goes on."""
+        try:
+            view = colours[1:-1, 1:-1] if self.edge_correction else colours
+            plotting.plot_slice(view, plotting.level_file(self.plot_path, water_level), self.plot_colour_map)
+        except Exception as err:
+            print(f"Could not make watershed plot. Error: {err}")
+
+    def _plot_pass(self, input: np.ndarray, seeds: Sequence) -> None:
+        """The reference routes transform / transform_history / transform_to_list through transform_with_hook
+        (lib.rs:1524-1560), so they plot too; here they have their own device paths, and with a plot folder set
+        one extra pass through the per-level hook makes the pictures."""
+        if self.plot_path is not None:
+            self._hook_run(input, seeds, None)
+
     def transform_with_hook(self, input: np.ndarray, seeds: Sequence) -> list:
+        return self._hook_run(input, seeds, self.wlvl_hook)
+
+    def _hook_run(self, input: np.ndarray, seeds: Sequence, hook) -> list:
         ctx = self._ctx()
         cfg, view, s = self._cfg(), N.image_view(input), N.seeds_array(seeds)
-        hook = self.wlvl_hook
+        plot = self.plot_path is not None
         results: list = []
         errors: list = []
         seed_cache: list = []
@@ -238,11 +274,14 @@ class Watershed(WatershedUtils, Generic[T]):
                 n = h.rows * h.cols
                 image = np.frombuffer((C.c_uint8 * n).from_address(h.image), dtype=np.uint8).reshape(h.rows, h.cols)
                 colours = np.frombuffer((C.c_uint64 * n).from_address(h.colours), dtype=np.uint64).reshape(h.rows, h.cols)
-                results.append(hook(HookCtx(h.water_level, h.max_water_level, image, colours, seed_list)))
+                if plot:
+                    self._plot_level(h.water_level, colours)
+                if hook is not None:
+                    results.append(hook(HookCtx(h.water_level, h.max_water_level, image, colours, seed_list)))
             except BaseException as e:  # never unwind through C
                 errors.append(e)
 
-        cb = N.HOOK_FN(_cb) if hook is not None else C.cast(None, N.HOOK_FN)
+        cb = N.HOOK_FN(_cb) if (hook is not None or plot) else C.cast(None, N.HOOK_FN)
         ctx.check(ctx.lib.ws_transform_with_hook(ctx.handle, C.byref(cfg), C.byref(view), s.ctypes.data,
                                                  s.shape[0], cb, None))
         if errors:
@@ -251,6 +290,7 @@ class Watershed(WatershedUtils, Generic[T]):
 
     # -- Watershed::transform_to_list -------------------------------------------
     def transform_to_list(self, input: np.ndarray, seeds: Sequence) -> List[Tuple[int, np.ndarray]]:
+        self._plot_pass(input, seeds)
         ctx = self._ctx()
         cfg, view, s = self._cfg(), N.image_view(input), N.seeds_array(seeds)
         r, c = self._out_shape(input)
@@ -262,6 +302,7 @@ class Watershed(WatershedUtils, Generic[T]):
 
     # -- Watershed::transform_history --------------------------------------------
     def transform_history(self, input: np.ndarray, seeds: Sequence) -> List[Tuple[int, np.ndarray]]:
+        self._plot_pass(input, seeds)
         ctx = self._ctx()
         cfg, view, s = self._cfg(), N.image_view(input), N.seeds_array(seeds)
         r, c = self._out_shape(input)
