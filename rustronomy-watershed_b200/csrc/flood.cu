@@ -499,7 +499,7 @@ struct FloodStage {  // (tensor copies want 128-byte aligned destinations)
 struct __align__(128) FloodSmem {
   FloodStage st[FLOOD_STAGES];
   uint32_t W[SM_H * SM_W];          // working tile incl. halo
-  uint8_t wpix[TILE_H * PIX_W];     // working image tile
+  size_t tbase[FLOOD_STAGES];       // per stage: word index of the tile's pixel (0, 0) in the padded arrival times
   uint64_t full[FLOOD_STAGES], empty[FLOOD_STAGES];  // mbarriers of the ring
   uint32_t tile[FLOOD_STAGES];
   uint32_t dirty[3];                // cells changed in a phase (rotating: written, read, cleared)
@@ -507,10 +507,51 @@ struct __align__(128) FloodSmem {
                                     // the pixel facing it (KEY_NONE: that neighbour need not re-run)
 };
 
-__device__ __forceinline__ uint32_t flood_A(uint32_t pix) { return pix == 255u ? T_INF : ((pix << 24) | 1u); }
+// A(p) = (img[p] << 24) | 1.  A pixel that can never flood is stored as 255 (fill_state): its A = 0xFF000001 lies
+// above T_INF = 0xFF000000, the value its arrival time starts with, so no relaxation ever lowers it -- no special
+// case needed.
+__device__ __forceinline__ uint32_t flood_A(uint32_t pix) { return (pix << 24) | 1u; }
+
+// one Gauss-Seidel step of a sweep: T(p) <- min(T(p), max(A(p), 1 + min(m, prev, next)))   (3 instructions)
+__device__ __forceinline__ uint32_t flood_relax(uint32_t t, uint32_t m, uint32_t prev, uint32_t nb, uint32_t A) {
+  return min(t, __viaddmax_u32(__vimin3_u32(m, prev, nb), 1u, A));
+}
+
+// One phase of a thread: two Gauss-Seidel sweeps (forwards, then backwards) over its 8 pixels along one axis
+// (ALONG = word stride between them, ACROSS = stride to the two neighbours off the axis).  Returns whether
+// any of the 8 changed.
+template <int ALONG, int ACROSS>
+__device__ __forceinline__ bool flood_phase(uint32_t* base, const uint32_t (&A)[ROWS_PER_THREAD]) {
+  uint32_t t[ROWS_PER_THREAD], o[ROWS_PER_THREAD], m[ROWS_PER_THREAD];
+  const uint32_t lo = base[-ALONG], hi = base[ROWS_PER_THREAD * ALONG];
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+    t[i] = o[i] = base[i * ALONG];
+    m[i] = min(base[i * ALONG - ACROSS], base[i * ALONG + ACROSS]);
+  }
+  uint32_t prev = lo;
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+    t[i] = flood_relax(t[i], m[i], prev, (i < ROWS_PER_THREAD - 1) ? t[i + 1] : hi, A[i]);
+    prev = t[i];
+  }
+  prev = hi;
+#pragma unroll
+  for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
+    t[i] = flood_relax(t[i], m[i], prev, (i > 0) ? t[i - 1] : lo, A[i]);
+    prev = t[i];
+  }
+  uint32_t x = 0u;
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) x |= t[i] ^ o[i];
+  if (x == 0u) return false;
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) base[i * ALONG] = t[i];
+  return true;
+}
 
 // ---- consumer side: one tile to its local fixed point ------------------------------------
-__device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm, int s, uint32_t tile) {
+__device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm, int s) {
   const ImageDims& d = a.d;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -525,15 +566,6 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
     dst[lane + 32] = src[lane + 32];
     if (lane < TILE_W + 2 - 64) dst[lane + 64] = src[lane + 64];
   }
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(st.pix);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sm.wpix);
-    for (int i = tid; i < TILE_H * TILE_W / 4; i += FLOOD_CONSUMERS) {
-      const int r = i / (TILE_W / 4), w = i - r * (TILE_W / 4);
-      dst[r * (PIX_W / 4) + w] = src[i];
-    }
-  }
-  consumer_sync();
 
   // column ownership: column cl, rows cgp*8 .. cgp*8+7;  row ownership: row rl, columns rgp*8 .. +7
   const int cl = tid % TILE_W, cgp = tid / TILE_W;
@@ -541,13 +573,19 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
   const int rl = lane, rgp = warp;
   uint32_t* rowp = sm.W + (rl + 1) * SM_W + rgp * ROWS_PER_THREAD + 1;
   uint32_t Ac[ROWS_PER_THREAD], Ar[ROWS_PER_THREAD];
+  {
+    // straight from the staged image bytes (dense rows of TILE_W): a thread's eight row-phase pixels are two
+    // aligned words, one byte permute each
+    const uint32_t* prow = reinterpret_cast<const uint32_t*>(st.pix + rl * TILE_W + rgp * ROWS_PER_THREAD);
+    const uint32_t w0 = prow[0], w1 = prow[1];
+    Ar[0] = __byte_perm(w0, 1u, 0x0554); Ar[1] = __byte_perm(w0, 1u, 0x1554);
+    Ar[2] = __byte_perm(w0, 1u, 0x2554); Ar[3] = __byte_perm(w0, 1u, 0x3554);
+    Ar[4] = __byte_perm(w1, 1u, 0x0554); Ar[5] = __byte_perm(w1, 1u, 0x1554);
+    Ar[6] = __byte_perm(w1, 1u, 0x2554); Ar[7] = __byte_perm(w1, 1u, 0x3554);
 #pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    Ac[i] = flood_A(sm.wpix[(cgp * ROWS_PER_THREAD + i) * PIX_W + cl]);
-    Ar[i] = flood_A(sm.wpix[rl * PIX_W + rgp * ROWS_PER_THREAD + i]);
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) Ac[i] = flood_A(st.pix[(cgp * ROWS_PER_THREAD + i) * TILE_W + cl]);
   }
 
-  bool ovf = false;
   uint32_t nphase = 0;
   // Dirty cells.  The tile is 4 x 8 cells of 8 x 8 pixels (bit = cell row * 8 + cell column).  A warp
   // iterates in a phase only if one of its four cells, or a cell next to them, changed in the previous
@@ -560,116 +598,71 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
   uint32_t active = 0xFFFFFFFFu;  // cells that changed in the previous phase, dilated by one cell
   if (tid == 0) sm.dirty[0] = sm.dirty[1] = sm.dirty[2] = 0u;
   consumer_sync();
-  for (uint32_t ph = 0;; ++ph) {
+  // dirty words rotate: written in this phase / written in the previous one (read after the barrier) / cleared now
+  uint32_t* dw = &sm.dirty[0];
+  uint32_t* dn1 = &sm.dirty[1];
+  uint32_t* dn2 = &sm.dirty[2];
+  for (bool colphase = true;; colphase = !colphase) {
     ++nphase;
-    uint32_t it = 0;
-    if ((ph & 1u) == 0u) {
-      if (active & col_cells) {
-        // ---- column phase: T(p) = max(A(p), 1 + min over the 4 neighbours) down then up ----
-        uint32_t t[ROWS_PER_THREAD], m[ROWS_PER_THREAD];
-        const uint32_t up = colp[-SM_W], dn = colp[ROWS_PER_THREAD * SM_W];
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          t[i] = colp[i * SM_W];
-          m[i] = min(colp[i * SM_W - 1], colp[i * SM_W + 1]);
-        }
-        uint32_t prev = up;
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          const uint32_t nb = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : dn;
-          const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ac[i]);  // max(A, 1 + min3)
-          if (n < t[i]) { t[i] = n; it |= 1u << i; }
-          prev = t[i];
-        }
-        prev = dn;
-#pragma unroll
-        for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
-          const uint32_t nb = (i > 0) ? t[i - 1] : up;
-          const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ac[i]);  // max(A, 1 + min3)
-          if (n < t[i]) { t[i] = n; it |= 1u << i; }
-          prev = t[i];
-        }
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i)
-          if (it & (1u << i)) colp[i * SM_W] = t[i];
-        const uint32_t wm = __reduce_or_sync(0xffffffffu, it ? col_bit : 0u);
-        if (lane == 0 && wm) atomicOr(&sm.dirty[ph % 3u], wm);
-      }
+    bool changed = false;
+    if (colphase) {
+      // column phase: down then up along the thread's 8 rows
+      if (active & col_cells) changed = flood_phase<SM_W, 1>(colp, Ac);
+      const uint32_t wm = __reduce_or_sync(0xffffffffu, changed ? col_bit : 0u);
+      if (lane == 0 && wm) atomicOr(dw, wm);
     } else {
-      if (active & row_cells) {
-        // ---- row phase: right then left ----------------------------------------------------
-        uint32_t t[ROWS_PER_THREAD], m[ROWS_PER_THREAD];
-        const uint32_t lf = rowp[-1], rt = rowp[ROWS_PER_THREAD];
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          t[i] = rowp[i];
-          m[i] = min(rowp[i - SM_W], rowp[i + SM_W]);
-        }
-        uint32_t prev = lf;
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-          const uint32_t nb = (i < ROWS_PER_THREAD - 1) ? t[i + 1] : rt;
-          const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ar[i]);
-          if (n < t[i]) { t[i] = n; it |= 1u << i; }
-          prev = t[i];
-        }
-        prev = rt;
-#pragma unroll
-        for (int i = ROWS_PER_THREAD - 1; i >= 0; --i) {
-          const uint32_t nb = (i > 0) ? t[i - 1] : lf;
-          const uint32_t n = __viaddmax_u32(__vimin3_u32(m[i], prev, nb), 1u, Ar[i]);
-          if (n < t[i]) { t[i] = n; it |= 1u << i; }
-          prev = t[i];
-        }
-#pragma unroll
-        for (int i = 0; i < ROWS_PER_THREAD; ++i)
-          if (it & (1u << i)) rowp[i] = t[i];
-        const uint32_t wm = __reduce_or_sync(0xffffffffu, it ? row_bit : 0u);
-        if (lane == 0 && wm) atomicOr(&sm.dirty[ph % 3u], wm);
-      }
+      // row phase: right then left along its 8 columns
+      if (active & row_cells) changed = flood_phase<1, SM_W>(rowp, Ar);
+      const uint32_t wm = __reduce_or_sync(0xffffffffu, changed ? row_bit : 0u);
+      if (lane == 0 && wm) atomicOr(dw, wm);
     }
-    if (tid == 0) sm.dirty[(ph + 1u) % 3u] = 0u;  // last read after the barrier of phase ph - 2
-    if (!consumer_sync_or(it != 0u)) break;
-    const uint32_t dm = sm.dirty[ph % 3u];
+    if (tid == 0) *dn2 = 0u;  // last read after the barrier of the phase before the previous one
+    if (!consumer_sync_or(changed)) break;
+    const uint32_t dm = *dw;
     active = dm | ((dm & ~0x80808080u) << 1) | ((dm & ~0x01010101u) >> 1) | (dm << 8) | (dm >> 8);
+    uint32_t* tmp = dn1; dn1 = dw; dw = dn2; dn2 = tmp;
   }
 
   // write back what changed against the staged copy (column ownership: coalesced along rows)
-  const int tpi = d.tiles_per_img();
-  const int img = tile / tpi;
-  const int trem = tile - img * tpi;
-  const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
-  uint32_t* Tg = a.b.T + (size_t)img * d.t_plane() +
-                 d.t_index(ty * TILE_H + cgp * ROWS_PER_THREAD, tx * TILE_W + cl);
+  uint32_t* Tg = a.b.T + sm.tbase[s] + (size_t)(cgp * ROWS_PER_THREAD) * d.t_pitch() + cl;
   const int tp = d.t_pitch();
-  // A neighbour tile re-runs only if a changed edge pixel can still lower the pixel facing it:
-  // T(edge) + 1 < T(facing pixel), the latter as staged in our halo (never newer than the truth, so the
-  // test never drops a needed wake-up).  Without it every tile woke all four neighbours, including the
-  // one its values came from, and most activations were such echoes.  The smallest such offer per
-  // direction is the priority of the wake-up.
-  uint32_t kl = KEY_NONE, kr = KEY_NONE, ku = KEY_NONE, kd = KEY_NONE;
+  uint32_t v[ROWS_PER_THREAD], chm = 0u;
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    const uint32_t v = colp[i * SM_W];
-    if (v != st.T[(cgp * ROWS_PER_THREAD + i + 1) * STG_W + cl + T_PAD_L]) {
-      // A hop counter that ran past 2^24 - 1 carries into the level and leaves hop == 0 behind: the pixel
-      // where that happens keeps this value (everything after it is built on it), so looking at the values
-      // that are written back is enough -- no test inside the relaxation.
-      ovf |= ((v & HOP_MASK) == 0u);
-      atomicMin(Tg + (size_t)i * tp, v);  // result unused: a fire-and-forget RED.MIN (measured: same time as st)
-      if (cl == 0 && v + 1u < colp[i * SM_W - 1]) kl = min(kl, v + 1u);
-      if (cl == TILE_W - 1 && v + 1u < colp[i * SM_W + 1]) kr = min(kr, v + 1u);
-      if (cgp == 0 && i == 0 && v + 1u < colp[-SM_W]) ku = v + 1u;
-      if (cgp == TILE_H / ROWS_PER_THREAD - 1 && i == ROWS_PER_THREAD - 1 && v + 1u < colp[ROWS_PER_THREAD * SM_W])
-        kd = v + 1u;
-    }
+    v[i] = colp[i * SM_W];
+    if (v[i] != st.T[(cgp * ROWS_PER_THREAD + i + 1) * STG_W + cl + T_PAD_L]) chm |= 1u << i;
   }
-  if (kl != KEY_NONE) atomicMin(&sm.key[s][DIR_LEFT], kl);
-  if (kr != KEY_NONE) atomicMin(&sm.key[s][DIR_RIGHT], kr);
-  if (ku != KEY_NONE) atomicMin(&sm.key[s][DIR_UP], ku);
-  if (kd != KEY_NONE) atomicMin(&sm.key[s][DIR_DOWN], kd);
+  if (chm) {
+    // A hop counter that ran past 2^24 - 1 carries into the level and leaves hop == 0 behind: the pixel
+    // where that happens keeps this value (everything after it is built on it), so looking at the values
+    // that are written back is enough -- no test inside the relaxation.
+    bool ovf = false;
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD; ++i)
+      if (chm & (1u << i)) {
+        atomicMin(Tg + (size_t)i * tp, v[i]);  // result unused: a fire-and-forget RED.MIN (measured: same time as st)
+        ovf |= (v[i] & HOP_MASK) == 0u;
+      }
+    if (a.check_overflow && ovf) atomicOr(&a.b.ctrl[FC_ERROR], 2u);
+    // A neighbour tile re-runs only if a changed edge pixel can still lower the pixel facing it:
+    // T(edge) + 1 < T(facing pixel), the latter as staged in our halo (never newer than the truth, so the
+    // test never drops a needed wake-up).  Without it every tile woke all four neighbours, including the
+    // one its values came from, and most activations were such echoes.  The smallest such offer per
+    // direction is the priority of the wake-up.  Only the threads that own edge pixels look.
+    if (cl == 0 || cl == TILE_W - 1) {
+      const int side = cl == 0 ? -1 : 1;
+      uint32_t k = KEY_NONE;
+#pragma unroll
+      for (int i = 0; i < ROWS_PER_THREAD; ++i)
+        if ((chm & (1u << i)) && v[i] + 1u < colp[i * SM_W + side]) k = min(k, v[i] + 1u);
+      if (k != KEY_NONE) atomicMin(&sm.key[s][cl == 0 ? DIR_LEFT : DIR_RIGHT], k);
+    }
+    if (cgp == 0 && (chm & 1u) && v[0] + 1u < colp[-SM_W]) atomicMin(&sm.key[s][DIR_UP], v[0] + 1u);
+    if (cgp == TILE_H / ROWS_PER_THREAD - 1 && (chm & (1u << (ROWS_PER_THREAD - 1))) &&
+        v[ROWS_PER_THREAD - 1] + 1u < colp[ROWS_PER_THREAD * SM_W])
+      atomicMin(&sm.key[s][DIR_DOWN], v[ROWS_PER_THREAD - 1] + 1u);
+  }
   if (tid == 0) atomicAdd(&a.b.ctrl[FC_PHASES], nphase);
-  if (a.check_overflow && ovf) atomicOr(&a.b.ctrl[FC_ERROR], 2u);
 }
 
 // ---- producer side: the worklist -----------------------------------------------------------
@@ -856,6 +849,13 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
       if (lane == 0) {
         if (idle) atomicAdd(&a.b.ctrl[FC_IDLE], idle);
         sm.tile[s] = tile;
+        if (tile != TILE_NONE) {
+          const int tpi = d.tiles_per_img();
+          const int img = tile / tpi;
+          const int trem = tile - img * tpi;
+          const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
+          sm.tbase[s] = (size_t)img * d.t_plane() + d.t_index(ty * TILE_H, tx * TILE_W);
+        }
         sm.key[s][0] = sm.key[s][1] = sm.key[s][2] = sm.key[s][3] = KEY_NONE;
       }
       if (tile == TILE_NONE) {
@@ -929,7 +929,7 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
       const long long t1 = clock64();
       const uint32_t tile = sm.tile[s];
       if (tile == TILE_NONE) break;
-      flood_consume(a, sm, s, tile);
+      flood_consume(a, sm, s);
       consumer_sync();  // all results of the tile issued, all reads of the stage done
       if (threadIdx.x == 0) mbar_arrive(&sm.empty[s]);
       waited += t1 - t0;

@@ -19,6 +19,10 @@ tiles = ((S + 63) // 64) * ((S + 31) // 32)
 print(kind, S, "seeds", n, st, ph)
 print("activations/tile %.2f  phases/activation %.2f  us per activation (444 CTAs) %.2f" % (
     st["tile_activations"] / tiles, st["flood_phases"] / st["tile_activations"], ph["flood"] * 1e3 * 444 / st["tile_activations"]))
+print("consumers: busy %.0f Mcyc, waiting %.0f Mcyc (%.0f %% waiting); busy cycles per activation %.0f, per phase %.0f" % (
+    st["flood_busy_kcycles"] / 1e3, st["flood_wait_kcycles"] / 1e3,
+    100.0 * st["flood_wait_kcycles"] / max(1, st["flood_wait_kcycles"] + st["flood_busy_kcycles"]),
+    st["flood_busy_kcycles"] * 1024.0 / st["tile_activations"], st["flood_busy_kcycles"] * 1024.0 / st["flood_phases"]))
 T = ctx.d2h(plan.arrival_times_ptr, (S, S), np.uint32)
 lv = T >> 24
 fin = lv < 255
