@@ -550,6 +550,11 @@ __device__ __forceinline__ bool flood_phase(uint32_t* base, const uint32_t (&A)[
   return true;
 }
 
+// cells (bit = cell row * 8 + cell column, 4 x 8 cells) and their four neighbours
+__device__ __forceinline__ uint32_t cells_dilate(uint32_t m) {
+  return m | ((m & ~0x80808080u) << 1) | ((m & ~0x01010101u) >> 1) | (m << 8) | (m >> 8);
+}
+
 // ---- consumer side: one tile to its local fixed point ------------------------------------
 __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm, int s) {
   const ImageDims& d = a.d;
@@ -595,42 +600,53 @@ __device__ __forceinline__ void flood_consume(const FloodArgs& a, FloodSmem& sm,
   const uint32_t col_bit = 1u << (cgp * 8 + cl / 8);
   const uint32_t row_cells = 0x01010101u << warp;                  // row phase: 32 rows, columns warp*8..
   const uint32_t row_bit = 1u << ((rl / 8) * 8 + rgp);
-  uint32_t active = 0xFFFFFFFFu;  // cells that changed in the previous phase, dilated by one cell
+  // "one of my cells or a cell next to them changed" == the changed cells meet my cells dilated by one cell
+  const uint32_t col_near = cells_dilate(col_cells), row_near = cells_dilate(row_cells);
+  uint32_t dm = 0xFFFFFFFFu;  // cells that changed in the previous phase
+  uint32_t ever = 0u;         // cells that changed in any phase
   if (tid == 0) sm.dirty[0] = sm.dirty[1] = sm.dirty[2] = 0u;
   consumer_sync();
-  // dirty words rotate: written in this phase / written in the previous one (read after the barrier) / cleared now
-  uint32_t* dw = &sm.dirty[0];
-  uint32_t* dn1 = &sm.dirty[1];
-  uint32_t* dn2 = &sm.dirty[2];
-  for (bool colphase = true;; colphase = !colphase) {
-    ++nphase;
-    bool changed = false;
-    if (colphase) {
-      // column phase: down then up along the thread's 8 rows
-      if (active & col_cells) changed = flood_phase<SM_W, 1>(colp, Ac);
+  // dirty words rotate: written in this phase (read after its barrier) / read in the previous phase / cleared now
+  for (int k = 0;; k = (k == 2) ? 0 : k + 1) {
+    uint32_t* dw = &sm.dirty[k];
+    // ---- column phase: down then up along the thread's 8 rows ----
+    {
+      ++nphase;
+      bool changed = false;
+      if (dm & col_near) changed = flood_phase<SM_W, 1>(colp, Ac);
       const uint32_t wm = __reduce_or_sync(0xffffffffu, changed ? col_bit : 0u);
       if (lane == 0 && wm) atomicOr(dw, wm);
-    } else {
-      // row phase: right then left along its 8 columns
-      if (active & row_cells) changed = flood_phase<1, SM_W>(rowp, Ar);
+      if (tid == 0) sm.dirty[k == 2 ? 0 : k + 1] = 0u;  // last read after the barrier of the previous phase
+      if (!consumer_sync_or(changed)) break;
+      dm = *dw;
+      ever |= dm;
+    }
+    k = (k == 2) ? 0 : k + 1;
+    dw = &sm.dirty[k];
+    // ---- row phase: right then left along its 8 columns ----
+    {
+      ++nphase;
+      bool changed = false;
+      if (dm & row_near) changed = flood_phase<1, SM_W>(rowp, Ar);
       const uint32_t wm = __reduce_or_sync(0xffffffffu, changed ? row_bit : 0u);
       if (lane == 0 && wm) atomicOr(dw, wm);
+      if (tid == 0) sm.dirty[k == 2 ? 0 : k + 1] = 0u;
+      if (!consumer_sync_or(changed)) break;
+      dm = *dw;
+      ever |= dm;
     }
-    if (tid == 0) *dn2 = 0u;  // last read after the barrier of the phase before the previous one
-    if (!consumer_sync_or(changed)) break;
-    const uint32_t dm = *dw;
-    active = dm | ((dm & ~0x80808080u) << 1) | ((dm & ~0x01010101u) >> 1) | (dm << 8) | (dm >> 8);
-    uint32_t* tmp = dn1; dn1 = dw; dw = dn2; dn2 = tmp;
   }
 
   // write back what changed against the staged copy (column ownership: coalesced along rows)
   uint32_t* Tg = a.b.T + sm.tbase[s] + (size_t)(cgp * ROWS_PER_THREAD) * d.t_pitch() + cl;
   const int tp = d.t_pitch();
   uint32_t v[ROWS_PER_THREAD], chm = 0u;
+  if (ever & col_bit) {  // else: nothing in the 8 x 8 cell of my pixels ever changed
 #pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    v[i] = colp[i * SM_W];
-    if (v[i] != st.T[(cgp * ROWS_PER_THREAD + i + 1) * STG_W + cl + T_PAD_L]) chm |= 1u << i;
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+      v[i] = colp[i * SM_W];
+      if (v[i] != st.T[(cgp * ROWS_PER_THREAD + i + 1) * STG_W + cl + T_PAD_L]) chm |= 1u << i;
+    }
   }
   if (chm) {
     // A hop counter that ran past 2^24 - 1 carries into the level and leaves hop == 0 behind: the pixel

@@ -30,10 +30,12 @@ constexpr int LT_THREADS = 256;
 constexpr int LT_W = STG_W;       // staged arrival times: rows of 72 words (image columns c0-4 .. c0+67)
 constexpr int LT_H = TILE_H + 2;
 constexpr int LT_C0 = T_PAD_L;    // staged column of the tile's column 0
-// working word of a pixel: LT_LOCAL | next pixel of its chain inside the tile (bits 31..30 = 01); anything else
-// is final: a colour (bit 31 set; bit 30 may belong to the colour) or a rim reference (< 2^28)
+// working word of a pixel: LT_LOCAL | BYTE offset of the next pixel of its chain inside the tile's word array;
+// anything else is final: a colour (bit 31 set: negative as a signed word) or a rim reference (< 2^28).  In-tile
+// pointers are the only words in [2^30, 2^31): one signed compare tells them apart.
 constexpr uint32_t LT_LOCAL = 0x40000000u;
-__device__ __forceinline__ bool lt_is_local(uint32_t w) { return (w >> 30) == 1u; }
+constexpr uint32_t LT_OFF_MASK = (TILE_H * TILE_W - 1) * 4;
+__device__ __forceinline__ bool lt_is_local(uint32_t w) { return (int32_t)w >= (int32_t)LT_LOCAL; }
 constexpr int RIM_PER_TILE = 2 * TILE_W + 2 * (TILE_H - 2);  // 188
 
 size_t rim_words(const ImageDims& d) { return (size_t)d.tiles_total() * RIM_PER_TILE + 2 * (size_t)d.cols; }
@@ -51,6 +53,7 @@ struct __align__(128) LabelSmem {
   uint32_t w[TILE_H * TILE_W];     // per pixel: LT_LOCAL | next pixel inside the tile, or its final word
   uint64_t bar;
   uint32_t nseed_px;
+  int img, ty, tx;
 };
 
 // counter-based generator of the random tie-break: splitmix64 of (key, position of the pixel in the field)
@@ -61,57 +64,37 @@ __device__ __forceinline__ uint32_t tie_hash(uint64_t key, uint64_t idx) {
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 
-template <bool kTieRandom>
-__global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, ImageDims d,
-                                                                uint32_t* __restrict__ ndistinct, uint64_t tie_seed) {
-  __shared__ LabelSmem sm;
+// The pixels of one thread (column lc, rows g*8 .. g*8+7): level byte, parent / colour word.  kPlain: the tile lies
+// completely inside the image and holds no halo row of a strip -- no per-pixel bounds or ownership tests.
+template <bool kTieRandom, bool kPlain>
+__device__ __forceinline__ uint32_t lt_parents(LabelSmem& sm, const FloodBuffers& b, const ImageDims& d, int img, int r0,
+                                               int c0, int tile, bool sorted, const uint32_t (&rb)[ROWS_PER_THREAD],
+                                               uint32_t col_first, uint64_t tie_seed) {
   const int tid = threadIdx.x;
-  const int tpi = d.tiles_per_img();
-  const int img = blockIdx.x / tpi;
-  const int trem = blockIdx.x - img * tpi;
-  const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
-  const int r0 = ty * TILE_H, c0 = tx * TILE_W;
-  const int tp = d.t_pitch();
-  // box rows r0-1 .. r0+32 (padded row index r0 .. r0+33), columns c0-4 .. c0+67: in bounds and 16-byte
-  // aligned in the padded layout; the flood's results were written by atomics (generic proxy) in an earlier
-  // launch, so no cross-proxy fence is needed here
-  const uint32_t* tsrc = b.T + (size_t)img * d.t_plane() + (size_t)r0 * tp + c0;
-  if (tid == 0) {
-    sm.nseed_px = 0;
-    mbar_init(&sm.bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_arrive_expect_tx(&sm.bar, LT_H * LT_W * 4);
-    for (int r = 0; r < LT_H; ++r) bulk_g2s(&sm.T[r * LT_W], tsrc + (size_t)r * tp, LT_W * 4, &sm.bar);
-  }
-  __syncthreads();  // the barrier is initialised before anyone waits on it
-  mbar_wait(&sm.bar, 0);
-
   const int lc = tid % TILE_W, g = tid / TILE_W;
   const size_t base = (size_t)img * d.px_per_img();
   const uint32_t rim_total = (uint32_t)d.tiles_total() * RIM_PER_TILE;
-  // Sorted seed list (flood.cu, fill_rows_kernel): a seed's colour is its position in the list -- the index of
-  // the row's first seed at or right of this warp's first column (rowbase, one entry per 32 columns), plus the
-  // seeds to its left among the warp's 32 columns (a warp holds one row, 32 consecutive columns, per step).
-  const bool sorted = __ldcg(&b.ctrl[FC_SEED_UNSORTED]) == 0u;
-  const int rb_pitch = 2 * d.tiles_x;
-  const uint32_t* rb_ptr = b.rowbase + ((size_t)img * d.rows + r0 + g * ROWS_PER_THREAD) * rb_pitch + 2 * tx + (lc >> 5);
-  const uint32_t col_first = b.colour_base + 1u - __ldg(b.seed_off + img);   // colour of the slice's seed 0, minus its index
   const int halo_a = d.halo_top ? 0 : -1, halo_b = d.halo_bottom ? d.rows - 1 : -1;   // this plan's halo rows
-  int nseed_px = 0;  // owned pixels that hold a seed (arrival time 0): the colours present on the canvas
+  // byte offsets (relative to a pixel's own word) that leave the tile from this thread's column / first / last row
+  constexpr int NEVER = 0x7FFFFFFF;
+  const int off_r = lc == TILE_W - 1 ? 4 : NEVER, off_l = lc == 0 ? -4 : NEVER;
+  const int off_d = g == TILE_H / ROWS_PER_THREAD - 1 ? TILE_W * 4 : NEVER, off_u = g == 0 ? -TILE_W * 4 : NEVER;
+  const uint32_t lane_lt = (1u << (tid & 31)) - 1u;
+  uint32_t nseed_warp = 0;  // owned pixels of the warp's rows that hold a seed (arrival time 0)
+  uint8_t* lvl_p = b.lvl + base + (size_t)(r0 + g * ROWS_PER_THREAD) * d.cols + c0 + lc;
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
     const int lr = g * ROWS_PER_THREAD + i;
-    const int li = lr * TILE_W + lc;
     const int r = r0 + lr, c = c0 + lc;
     uint32_t term = LAB_RESOLVED;  // UNCOLOURED
     const uint32_t* t = sm.T + (lr + 1) * LT_W + lc + LT_C0;
     const uint32_t tv = t[0];
-    const bool inside = r < d.rows && c < d.cols;
-    const bool halo = r == halo_a || r == halo_b;
+    const bool inside = kPlain || (r < d.rows && c < d.cols);
+    const bool halo = !kPlain && (r == halo_a || r == halo_b);
     const uint32_t seeds_here = __ballot_sync(0xffffffffu, inside && tv == 0u && !halo);
+    nseed_warp += (uint32_t)__popc(seeds_here);
     if (inside) {
-      const size_t p = base + (size_t)r * d.cols + c;
-      b.lvl[p] = (tv >= T_INF) ? (uint8_t)255 : (uint8_t)(tv >> 24);
+      lvl_p[(size_t)i * d.cols] = (uint8_t)(tv >> 24);   // T >= T_INF ("never") reads as level 255
       if (halo) {
         // a neighbouring strip owns this pixel: its slot behind the rim entries holds its own index ("pending")
         // until that strip's colour is imported; a pixel that is never coloured is resolved (UNCOLOURED) at once
@@ -121,58 +104,102 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
       } else if (tv >= T_INF) {
         // never coloured
       } else if (tv == 0u) {
-        if (sorted) {
-          const uint32_t left = (uint32_t)__popc(seeds_here & ((1u << (lc & 31)) - 1u));
-          term = LAB_RESOLVED | (col_first + __ldg(rb_ptr + i * rb_pitch) + left);
-        } else {
-          term = __ldcg(b.lab + p);  // seed: coloured by seed_init
-        }
-        ++nseed_px;
+        if (sorted) term = LAB_RESOLVED | (col_first + rb[i] + (uint32_t)__popc(seeds_here & lane_lt));
+        else term = __ldcg(b.lab + base + (size_t)r * d.cols + c);  // seed: coloured by seed_init
       } else {
-        // A coloured non-seed pixel is interior, so all four neighbours exist.
-        int dr = 0, dc = 0;
+        // A coloured non-seed pixel is interior, so all four neighbours exist.  Byte offset of the parent's word:
+        int off = 0;
+        const uint32_t dn = t[LT_W], rt = t[1], lf = t[-1], up = t[-LT_W];
         if (kTieRandom) {
           // the reference draws uniformly among the coloured neighbours, in the order down, right, left, up
-          const uint32_t em = (t[LT_W] < tv ? 1u : 0u) | (t[1] < tv ? 2u : 0u) | (t[-1] < tv ? 4u : 0u) |
-                              (t[-LT_W] < tv ? 8u : 0u);
+          const uint32_t em = (dn < tv ? 1u : 0u) | (rt < tv ? 2u : 0u) | (lf < tv ? 4u : 0u) | (up < tv ? 8u : 0u);
           const int k = __popc(em);
-          if (k == 0) {
-            atomicOr(&b.ctrl[FC_ERROR], 4u);
-          } else {
+          if (k) {
             int pick = 0;
             if (k > 1) {
               const uint64_t pos = ((uint64_t)img * (uint64_t)d.global_rows + (uint64_t)(r + d.row_offset)) * (uint64_t)d.cols + (uint64_t)c;
               pick = (int)(((uint64_t)tie_hash(tie_seed, pos) * (uint64_t)k) >> 32);
             }
             const int bit = __fns(em, 0, pick + 1);  // position of the pick-th set bit
-            dr = bit == 0 ? 1 : (bit == 3 ? -1 : 0);
-            dc = bit == 1 ? 1 : (bit == 2 ? -1 : 0);
+            off = bit == 0 ? TILE_W * 4 : (bit == 1 ? 4 : (bit == 2 ? -4 : -TILE_W * 4));
           }
-        } else if (t[LT_W] < tv) dr = 1;
-        else if (t[1] < tv) dc = 1;
-        else if (t[-1] < tv) dc = -1;
-        else if (t[-LT_W] < tv) dr = -1;
-        else atomicOr(&b.ctrl[FC_ERROR], 4u);  // cannot happen at a fixed point
-        const int pr = lr + dr, pc = lc + dc;
-        if (dr == 0 && dc == 0) {
-          // leave UNCOLOURED
-        } else if (pr >= 0 && pr < TILE_H && pc >= 0 && pc < TILE_W) {
-          term = LT_LOCAL | (uint32_t)(pr * TILE_W + pc);
+        } else {
+          // canonical: the first coloured neighbour in that order (the last assignment wins)
+          off = up < tv ? -TILE_W * 4 : off;
+          off = lf < tv ? -4 : off;
+          off = rt < tv ? 4 : off;
+          off = dn < tv ? TILE_W * 4 : off;
+        }
+        bool leaves = off == off_r || off == off_l;
+        if (i == 0) leaves |= off == off_u;
+        if (i == ROWS_PER_THREAD - 1) leaves |= off == off_d;
+        if (off == 0) {
+          atomicOr(&b.ctrl[FC_ERROR], 4u);  // cannot happen at a fixed point; the pixel stays UNCOLOURED
+        } else if (!leaves) {
+          term = (uint32_t)((int)(LT_LOCAL | (uint32_t)((lr * TILE_W + lc) * 4)) + off);
         } else {
           // the chain leaves the tile here, onto the rim of the neighbouring tile
-          const int ntile = blockIdx.x + dr * d.tiles_x + dc;
-          term = (uint32_t)ntile * RIM_PER_TILE + (uint32_t)rim_index(pr & (TILE_H - 1), pc & (TILE_W - 1));
+          const int dr = off == TILE_W * 4 ? 1 : (off == -TILE_W * 4 ? -1 : 0), dc = off == 4 ? 1 : (off == -4 ? -1 : 0);
+          const int ntile = tile + dr * d.tiles_x + dc;
+          term = (uint32_t)ntile * RIM_PER_TILE + (uint32_t)rim_index((lr + dr) & (TILE_H - 1), (lc + dc) & (TILE_W - 1));
         }
       }
     }
-    sm.w[li] = term;
+    sm.w[lr * TILE_W + lc] = term;
   }
+  return nseed_warp;
+}
+
+template <bool kTieRandom>
+__global__ void __launch_bounds__(LT_THREADS, 6) label_tile_kernel(FloodBuffers b, ImageDims d,
+                                                                uint32_t* __restrict__ ndistinct, uint64_t tie_seed) {
+  __shared__ LabelSmem sm;
+  const int tid = threadIdx.x;
+  const int tp = d.t_pitch();
+  if (tid == 0) {
+    const int tpi = d.tiles_per_img();
+    const int img = blockIdx.x / tpi;
+    const int trem = blockIdx.x - img * tpi;
+    const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
+    sm.img = img; sm.ty = ty; sm.tx = tx;
+    // box rows r0-1 .. r0+32 (padded row index r0 .. r0+33), columns c0-4 .. c0+67: in bounds and 16-byte
+    // aligned in the padded layout; the flood's results were written by atomics (generic proxy) in an earlier
+    // launch, so no cross-proxy fence is needed here
+    const uint32_t* tsrc = b.T + (size_t)img * d.t_plane() + (size_t)(ty * TILE_H) * tp + tx * TILE_W;
+    sm.nseed_px = 0;
+    mbar_init(&sm.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive_expect_tx(&sm.bar, LT_H * LT_W * 4);
+    for (int r = 0; r < LT_H; ++r) bulk_g2s(&sm.T[r * LT_W], tsrc + (size_t)r * tp, LT_W * 4, &sm.bar);
+  }
+  __syncthreads();  // the barrier is initialised before anyone waits on it
+  const int img = sm.img, ty = sm.ty, tx = sm.tx;
+  const int r0 = ty * TILE_H, c0 = tx * TILE_W;
+  const int lc = tid % TILE_W, g = tid / TILE_W;
+  const size_t base = (size_t)img * d.px_per_img();
+  // Sorted seed list (flood.cu, fill_rows_kernel): a seed's colour is its position in the list -- the index of
+  // the row's first seed at or right of this warp's first column (rowbase, one entry per 32 columns), plus the
+  // seeds to its left among the warp's 32 columns (a warp holds one row, 32 consecutive columns, per step).
+  // Loaded before the arrival times are waited for: nearly every warp of a noise field meets a seed.
+  const bool plain = r0 + TILE_H <= d.rows && c0 + TILE_W <= d.cols && !(d.halo_top && ty == 0) &&
+                     !(d.halo_bottom && r0 + TILE_H >= d.rows);
+  const bool sorted = __ldcg(&b.ctrl[FC_SEED_UNSORTED]) == 0u;
+  const uint32_t col_first = b.colour_base + 1u - __ldg(b.seed_off + img);   // colour of the slice's seed 0, minus its index
+  uint32_t rb[ROWS_PER_THREAD];
   {
-    // (a later duplicate seed overwrites an earlier one, lib.rs:1365-1367, so a pixel counts once)
+    const int rb_pitch = 2 * d.tiles_x;
+    const uint32_t* rb_ptr = b.rowbase + ((size_t)img * d.rows + r0 + g * ROWS_PER_THREAD) * rb_pitch + 2 * tx + (lc >> 5);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) nseed_px += __shfl_xor_sync(0xffffffffu, nseed_px, o);
-    if ((tid & 31) == 0 && nseed_px) atomicAdd(&sm.nseed_px, (uint32_t)nseed_px);
+    for (int i = 0; i < ROWS_PER_THREAD; ++i)
+      rb[i] = (sorted && r0 + g * ROWS_PER_THREAD + i < d.rows) ? __ldg(rb_ptr + (size_t)i * rb_pitch) : 0u;
   }
+  mbar_wait(&sm.bar, 0);
+
+  uint32_t nseed_warp;
+  if (plain) nseed_warp = lt_parents<kTieRandom, true>(sm, b, d, img, r0, c0, blockIdx.x, sorted, rb, col_first, tie_seed);
+  else nseed_warp = lt_parents<kTieRandom, false>(sm, b, d, img, r0, c0, blockIdx.x, sorted, rb, col_first, tie_seed);
+  // (a later duplicate seed overwrites an earlier one, lib.rs:1365-1367, so a pixel counts once)
+  if ((tid & 31) == 0 && nseed_warp) atomicAdd(&sm.nseed_px, nseed_warp);
   __syncthreads();
   if (tid == 0 && sm.nseed_px) atomicAdd(&ndistinct[img], sm.nseed_px);  // one global atomic per tile
 
@@ -182,10 +209,12 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
   // threads are active -- after two or three rounds on a noise field, whose chains are a few pixels long -- the
   // rest is walked sequentially, without barriers: a word only ever changes from a pointer to the final word of
   // its own chain, so whatever a racing reader sees is a valid successor or the end.
+  const char* wbytes = reinterpret_cast<const char*>(sm.w);
+  uint32_t* mine = sm.w + g * ROWS_PER_THREAD * TILE_W + lc;
   uint32_t act = 0, cur[ROWS_PER_THREAD];
 #pragma unroll
   for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    cur[i] = sm.w[(g * ROWS_PER_THREAD + i) * TILE_W + lc];
+    cur[i] = mine[i * TILE_W];
     if (lt_is_local(cur[i])) act |= 1u << i;
   }
   for (;;) {
@@ -196,29 +225,35 @@ __global__ void __launch_bounds__(LT_THREADS) label_tile_kernel(FloodBuffers b, 
       for (int i = 0; i < ROWS_PER_THREAD; ++i) {
         if (!(act & (1u << i))) continue;
         uint32_t x = cur[i];
-        while (lt_is_local(x)) x = ((volatile uint32_t*)sm.w)[x & (TILE_H * TILE_W - 1)];
-        sm.w[(g * ROWS_PER_THREAD + i) * TILE_W + lc] = x;
+        while (lt_is_local(x)) x = *reinterpret_cast<const volatile uint32_t*>(wbytes + (x & LT_OFF_MASK));
+        mine[i * TILE_W] = x;
       }
       __syncthreads();
       break;
     }
 #pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i)
-      if (act & (1u << i)) cur[i] = sm.w[cur[i] & (TILE_H * TILE_W - 1)];  // my successor's word: its successor, or the end
+    for (int i = 0; i < ROWS_PER_THREAD; ++i)   // my successor's word: its successor, or the end
+      if (act & (1u << i)) cur[i] = *reinterpret_cast<const uint32_t*>(wbytes + (cur[i] & LT_OFF_MASK));
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < ROWS_PER_THREAD; ++i) {
       if (!(act & (1u << i))) continue;
-      sm.w[(g * ROWS_PER_THREAD + i) * TILE_W + lc] = cur[i];
+      mine[i * TILE_W] = cur[i];
       if (!lt_is_local(cur[i])) act &= ~(1u << i);
     }
   }
 
+  if (plain) {
+    uint32_t* out = b.lab + base + (size_t)(r0 + g * ROWS_PER_THREAD) * d.cols + c0 + lc;
 #pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    const int lr = g * ROWS_PER_THREAD + i;
-    const int r = r0 + lr, c = c0 + lc;
-    if (r < d.rows && c < d.cols) __stcg(b.lab + base + (size_t)r * d.cols + c, sm.w[lr * TILE_W + lc]);
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) __stcg(out + (size_t)i * d.cols, mine[i * TILE_W]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD; ++i) {
+      const int lr = g * ROWS_PER_THREAD + i;
+      const int r = r0 + lr, c = c0 + lc;
+      if (r < d.rows && c < d.cols) __stcg(b.lab + base + (size_t)r * d.cols + c, sm.w[lr * TILE_W + lc]);
+    }
   }
   // the tile's rim, compact (pixels outside the image: UNCOLOURED, so that every entry is defined)
   if (tid < RIM_PER_TILE) {
