@@ -661,6 +661,13 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   p->stats[5] = p->h_ctrl[FC_PHASES];
   p->stats[6] = p->h_ctrl[FC_WAIT_KCYC];
   p->stats[7] = p->h_ctrl[FC_BUSY_KCYC];
+  {
+    static const bool env = [] { const char* e = getenv("WS_FLOOD_STATS"); return e && atoi(e) != 0; }();
+    if (env)
+      fprintf(stderr, "[ws] flood: %u activations, %u phases, %u stale; consumers busy %u waiting %u, producers idle %u (kilo-cycles)\n",
+              p->h_ctrl[FC_ACTIVATIONS], p->h_ctrl[FC_PHASES], p->h_ctrl[FC_STALE], p->h_ctrl[FC_BUSY_KCYC],
+              p->h_ctrl[FC_WAIT_KCYC], p->h_ctrl[FC_IDLE]);
+  }
   const uint32_t err = p->h_ctrl[FC_ERROR];
   if (err & 1u) return fail(ctx, WS_ERR_SEED_OOB, "a seed lies outside the image");
   if (err & 2u) return fail(ctx, WS_ERR_HOP_OVERFLOW, ws_status_str(WS_ERR_HOP_OVERFLOW));

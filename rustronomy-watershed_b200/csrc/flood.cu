@@ -819,6 +819,7 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
       // claim a tile; while there is none, finish the other stage (its pushes may be the next work)
       uint32_t tile = TILE_NONE;
       uint32_t idle = 0, stalled = 0, seen_activations = 0xFFFFFFFFu;
+      long long idle_since = 0;  // clock of the first claim that found the worklist empty
       for (;;) {
         if (q_i < q_n) {
           tile = __shfl_sync(0xffffffffu, q_tile, q_i);
@@ -832,6 +833,7 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
         q_n = flood_pop(a.b, lane, q_tile);
         q_i = 0;
         if (q_n) continue;
+        if (idle_since == 0) idle_since = clock64();
         bool busy = false, retired = false;
         for (int k = 1; k < FLOOD_STAGES && !retired; ++k) {  // the other stages, oldest first
           const int o = (s + k) % FLOOD_STAGES;
@@ -863,7 +865,7 @@ __global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_co
         }
       }
       if (lane == 0) {
-        if (idle) atomicAdd(&a.b.ctrl[FC_IDLE], idle);
+        if (idle_since) atomicAdd(&a.b.ctrl[FC_IDLE], (uint32_t)((clock64() - idle_since) >> 10));
         sm.tile[s] = tile;
         if (tile != TILE_NONE) {
           const int tpi = d.tiles_per_img();

@@ -11,7 +11,7 @@ enum FloodCtrl {
   FC_ACTIVATIONS = 0,  // tiles taken from the worklist and iterated            (statistics: words 0..7 are
   FC_PHASES = 1,       // in-tile phases run                                      reset before every flood launch
   FC_STALE = 2,        // worklist entries dropped because nothing new had arrived  of a strip import)
-  FC_IDLE = 3,         // idle polls of the producer warps
+  FC_IDLE = 3,         // producer warps: kilo-cycles between finding the worklist empty and the next claim
   FC_WAIT_KCYC = 4,    // consumers: kilo-cycles waiting for a staged tile (tail at the end of the flood excluded)
   FC_BUSY_KCYC = 5,    // consumers: kilo-cycles iterating
   FC_SEED_DUP = 7,     // seed_init saw a seed position twice (the statistics words 0..7 are reset per launch)
