@@ -636,7 +636,7 @@ extern "C" ws_status ws_plan_run(ws_plan* p, const ws_config* cfg, const uint8_t
   WS_CUDA(ctx, launch_flood(p->fb, p->d, check_ovf, p->bucket_shift, ctx->flood_grid, p->tmaps, s));
   WS_CUDA(ctx, cudaEventRecord(p->ev[2], s));
   WS_CUDA(ctx, cudaEventRecord(p->kev[3], s));
-  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, cfg->tie_break == WS_TIE_RANDOM, ctx->tie_seed, s));
+  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, cfg->tie_break == WS_TIE_RANDOM, ctx->tie_seed, p->tmaps, s));
   WS_CUDA(ctx, cudaEventRecord(p->kev[4], s));
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, 0, s));
   WS_CUDA(ctx, cudaEventRecord(p->kev[5], s));
@@ -926,7 +926,7 @@ static ws_status strip_labels_impl(ws_plan* p, bool sync) {
   if (!p) return WS_ERR_INVALID_ARG;
   ws_ctx* ctx = p->ctx;
   WS_CUDA(ctx, cudaSetDevice(ctx->device));
-  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, p->cfg.tie_break == WS_TIE_RANDOM, ctx->tie_seed, ctx->stream));
+  WS_CUDA(ctx, launch_parent(p->fb, p->d, p->mb.ndistinct, p->cfg.tie_break == WS_TIE_RANDOM, ctx->tie_seed, p->tmaps, ctx->stream));
   // asynchronous protocol: the label plane is finished once, after the last exchange round
   WS_CUDA(ctx, launch_jump(p->fb, p->d, ctx->jump_grid, sync ? 1 : 0, ctx->stream));
   p->stats[4] += 2;

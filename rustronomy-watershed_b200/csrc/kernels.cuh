@@ -109,6 +109,7 @@ size_t rim_words(const ImageDims& d);
 // also counts, per slice, the owned pixels that hold a seed = colours present on the canvas (ndistinct[n_img])
 // tie_random: draw the parent uniformly among the earlier neighbours (lib.rs:250-253) instead of taking the first
 cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, bool tie_random, uint64_t tie_seed,
+                          const void* tensor_maps,
                           cudaStream_t s);
 cudaError_t launch_jump(FloodBuffers b, ImageDims d, int grid, int finish, cudaStream_t s);
 cudaError_t launch_label_finish(FloodBuffers b, ImageDims d, int sms, cudaStream_t s);

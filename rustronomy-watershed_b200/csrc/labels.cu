@@ -21,6 +21,9 @@
 #include "kernels.cuh"
 
 #include <cooperative_groups.h>
+#include <cuda.h>  // CUtensorMap (type only)
+
+#include <cstring>
 
 namespace cg = cooperative_groups;
 
@@ -52,6 +55,7 @@ struct __align__(128) LabelSmem {
   uint32_t T[LT_H * LT_W];
   uint32_t w[TILE_H * TILE_W];     // per pixel: LT_LOCAL | next pixel inside the tile, or its final word
   uint64_t bar;
+  uint32_t rb[2 * TILE_H];        // sorted seed lists: rowbase of the tile's rows, one word per 32 columns
   uint32_t nseed_px;
   int img, ty, tx;
 };
@@ -68,8 +72,7 @@ __device__ __forceinline__ uint32_t tie_hash(uint64_t key, uint64_t idx) {
 // completely inside the image and holds no halo row of a strip -- no per-pixel bounds or ownership tests.
 template <bool kTieRandom, bool kPlain>
 __device__ __forceinline__ uint32_t lt_parents(LabelSmem& sm, const FloodBuffers& b, const ImageDims& d, int img, int r0,
-                                               int c0, int tile, bool sorted, const uint32_t (&rb)[ROWS_PER_THREAD],
-                                               uint32_t col_first, uint64_t tie_seed) {
+                                               int c0, int tile, bool sorted, uint32_t col_first, uint64_t tie_seed) {
   const int tid = threadIdx.x;
   const int lc = tid % TILE_W, g = tid / TILE_W;
   const size_t base = (size_t)img * d.px_per_img();
@@ -104,7 +107,7 @@ __device__ __forceinline__ uint32_t lt_parents(LabelSmem& sm, const FloodBuffers
       } else if (tv >= T_INF) {
         // never coloured
       } else if (tv == 0u) {
-        if (sorted) term = LAB_RESOLVED | (col_first + rb[i] + (uint32_t)__popc(seeds_here & lane_lt));
+        if (sorted) term = LAB_RESOLVED | (col_first + sm.rb[2 * lr + (lc >> 5)] + (uint32_t)__popc(seeds_here & lane_lt));
         else term = __ldcg(b.lab + base + (size_t)r * d.cols + c);  // seed: coloured by seed_init
       } else {
         // A coloured non-seed pixel is interior, so all four neighbours exist.  Byte offset of the parent's word:
@@ -150,98 +153,85 @@ __device__ __forceinline__ uint32_t lt_parents(LabelSmem& sm, const FloodBuffers
   return nseed_warp;
 }
 
+// one instruction per tile: 2-D tiled tensor copy global -> shared, completes on `bar` (the flood's map of the
+// arrival-time plane: box STG_W x STG_H = LT_W x LT_H)
+__device__ __forceinline__ void lt_tensor_g2s(void* dst, const CUtensorMap* tm, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
 template <bool kTieRandom>
-__global__ void __launch_bounds__(LT_THREADS, 6) label_tile_kernel(FloodBuffers b, ImageDims d,
-                                                                uint32_t* __restrict__ ndistinct, uint64_t tie_seed) {
+__global__ void __launch_bounds__(LT_THREADS, 6) label_tile_kernel(const __grid_constant__ CUtensorMap tmT, FloodBuffers b,
+                                                                   ImageDims d, uint32_t* __restrict__ ndistinct,
+                                                                   uint64_t tie_seed) {
   __shared__ LabelSmem sm;
   const int tid = threadIdx.x;
-  const int tp = d.t_pitch();
+  const int tpi = d.tiles_per_img();
+  const int img = blockIdx.x / tpi;
+  const int trem = blockIdx.x - img * tpi;
+  const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
+  const int r0 = ty * TILE_H, c0 = tx * TILE_W;
   if (tid == 0) {
-    const int tpi = d.tiles_per_img();
-    const int img = blockIdx.x / tpi;
-    const int trem = blockIdx.x - img * tpi;
-    const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
-    sm.img = img; sm.ty = ty; sm.tx = tx;
-    // box rows r0-1 .. r0+32 (padded row index r0 .. r0+33), columns c0-4 .. c0+67: in bounds and 16-byte
-    // aligned in the padded layout; the flood's results were written by atomics (generic proxy) in an earlier
-    // launch, so no cross-proxy fence is needed here
-    const uint32_t* tsrc = b.T + (size_t)img * d.t_plane() + (size_t)(ty * TILE_H) * tp + tx * TILE_W;
+    // box rows r0-1 .. r0+32 (padded row index r0 .. r0+33), columns c0-4 .. c0+67; the flood's results were
+    // written by atomics (generic proxy) in an earlier launch, so no cross-proxy fence is needed here
     sm.nseed_px = 0;
     mbar_init(&sm.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_arrive_expect_tx(&sm.bar, LT_H * LT_W * 4);
-    for (int r = 0; r < LT_H; ++r) bulk_g2s(&sm.T[r * LT_W], tsrc + (size_t)r * tp, LT_W * 4, &sm.bar);
+    lt_tensor_g2s(sm.T, &tmT, c0, img * d.t_rows() + r0, &sm.bar);
   }
-  __syncthreads();  // the barrier is initialised before anyone waits on it
-  const int img = sm.img, ty = sm.ty, tx = sm.tx;
-  const int r0 = ty * TILE_H, c0 = tx * TILE_W;
-  const int lc = tid % TILE_W, g = tid / TILE_W;
-  const size_t base = (size_t)img * d.px_per_img();
   // Sorted seed list (flood.cu, fill_rows_kernel): a seed's colour is its position in the list -- the index of
   // the row's first seed at or right of this warp's first column (rowbase, one entry per 32 columns), plus the
   // seeds to its left among the warp's 32 columns (a warp holds one row, 32 consecutive columns, per step).
-  // Loaded before the arrival times are waited for: nearly every warp of a noise field meets a seed.
+  const bool sorted = __ldcg(&b.ctrl[FC_SEED_UNSORTED]) == 0u;
+  if (tid < 2 * TILE_H) {
+    const int row = r0 + (tid >> 1);
+    sm.rb[tid] = (sorted && row < d.rows)
+                     ? __ldg(b.rowbase + ((size_t)img * d.rows + row) * (size_t)(2 * d.tiles_x) + 2 * tx + (tid & 1))
+                     : 0u;
+  }
+  __syncthreads();  // the barrier is initialised before anyone waits on it; rb[] is complete
+  const int lc = tid % TILE_W, g = tid / TILE_W;
+  const size_t base = (size_t)img * d.px_per_img();
   const bool plain = r0 + TILE_H <= d.rows && c0 + TILE_W <= d.cols && !(d.halo_top && ty == 0) &&
                      !(d.halo_bottom && r0 + TILE_H >= d.rows);
-  const bool sorted = __ldcg(&b.ctrl[FC_SEED_UNSORTED]) == 0u;
   const uint32_t col_first = b.colour_base + 1u - __ldg(b.seed_off + img);   // colour of the slice's seed 0, minus its index
-  uint32_t rb[ROWS_PER_THREAD];
-  {
-    const int rb_pitch = 2 * d.tiles_x;
-    const uint32_t* rb_ptr = b.rowbase + ((size_t)img * d.rows + r0 + g * ROWS_PER_THREAD) * rb_pitch + 2 * tx + (lc >> 5);
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i)
-      rb[i] = (sorted && r0 + g * ROWS_PER_THREAD + i < d.rows) ? __ldg(rb_ptr + (size_t)i * rb_pitch) : 0u;
-  }
   mbar_wait(&sm.bar, 0);
 
   uint32_t nseed_warp;
-  if (plain) nseed_warp = lt_parents<kTieRandom, true>(sm, b, d, img, r0, c0, blockIdx.x, sorted, rb, col_first, tie_seed);
-  else nseed_warp = lt_parents<kTieRandom, false>(sm, b, d, img, r0, c0, blockIdx.x, sorted, rb, col_first, tie_seed);
+  if (plain) nseed_warp = lt_parents<kTieRandom, true>(sm, b, d, img, r0, c0, blockIdx.x, sorted, col_first, tie_seed);
+  else nseed_warp = lt_parents<kTieRandom, false>(sm, b, d, img, r0, c0, blockIdx.x, sorted, col_first, tie_seed);
   // (a later duplicate seed overwrites an earlier one, lib.rs:1365-1367, so a pixel counts once)
   if ((tid & 31) == 0 && nseed_warp) atomicAdd(&sm.nseed_px, nseed_warp);
   __syncthreads();
   if (tid == 0 && sm.nseed_px) atomicAdd(&ndistinct[img], sm.nseed_px);  // one global atomic per tile
 
-  // Pointer jumping inside the tile; `act` = my pixels that still hold an in-tile pointer.  Rounds of doubling
-  // (reads and writes separated by barriers) while many threads have work: a round costs every thread its
-  // eight bit tests and two barriers whether or not it has anything left.  Once fewer than a quarter of the
-  // threads are active -- after two or three rounds on a noise field, whose chains are a few pixels long -- the
-  // rest is walked sequentially, without barriers: a word only ever changes from a pointer to the final word of
-  // its own chain, so whatever a racing reader sees is a valid successor or the end.
+  // Pointer jumping inside the tile, without barriers: every thread keeps replacing the words of its pixels by
+  // their successors' CURRENT words until none of them is an in-tile pointer any more.  A word only ever changes
+  // from a pointer to a pointer further down its own chain or to the chain's final word, so whatever a racing
+  // reader sees is a valid ancestor; chains shorten for everybody as results land (rounds of doubling separated
+  // by barriers cost two barriers and eight bit tests per round and thread, whether or not it had work left).
   const char* wbytes = reinterpret_cast<const char*>(sm.w);
   uint32_t* mine = sm.w + g * ROWS_PER_THREAD * TILE_W + lc;
-  uint32_t act = 0, cur[ROWS_PER_THREAD];
+  uint32_t cur[ROWS_PER_THREAD];
 #pragma unroll
-  for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-    cur[i] = mine[i * TILE_W];
-    if (lt_is_local(cur[i])) act |= 1u << i;
-  }
+  for (int i = 0; i < ROWS_PER_THREAD; ++i) cur[i] = mine[i * TILE_W];
   for (;;) {
-    const int nact = __syncthreads_count(act != 0u);
-    if (nact == 0) break;
-    if (nact < LT_THREADS / 4) {
-#pragma unroll
-      for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-        if (!(act & (1u << i))) continue;
-        uint32_t x = cur[i];
-        while (lt_is_local(x)) x = *reinterpret_cast<const volatile uint32_t*>(wbytes + (x & LT_OFF_MASK));
-        mine[i * TILE_W] = x;
-      }
-      __syncthreads();
-      break;
-    }
-#pragma unroll
-    for (int i = 0; i < ROWS_PER_THREAD; ++i)   // my successor's word: its successor, or the end
-      if (act & (1u << i)) cur[i] = *reinterpret_cast<const uint32_t*>(wbytes + (cur[i] & LT_OFF_MASK));
-    __syncthreads();
+    int top = (int)0x80000000;  // in-tile pointers are the largest words as signed numbers
 #pragma unroll
     for (int i = 0; i < ROWS_PER_THREAD; ++i) {
-      if (!(act & (1u << i))) continue;
-      mine[i * TILE_W] = cur[i];
-      if (!lt_is_local(cur[i])) act &= ~(1u << i);
+      if (lt_is_local(cur[i])) {
+        cur[i] = *reinterpret_cast<const volatile uint32_t*>(wbytes + (cur[i] & LT_OFF_MASK));
+        *reinterpret_cast<volatile uint32_t*>(mine + i * TILE_W) = cur[i];
+      }
+      top = max(top, (int)cur[i]);
     }
+    if (top < (int)LT_LOCAL) break;
   }
+  __syncthreads();  // the rim entries below are other threads' words
 
   if (plain) {
     uint32_t* out = b.lab + base + (size_t)(r0 + g * ROWS_PER_THREAD) * d.cols + c0 + lc;
@@ -268,14 +258,16 @@ __global__ void __launch_bounds__(LT_THREADS, 6) label_tile_kernel(FloodBuffers 
 }
 
 cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, bool tie_random, uint64_t tie_seed,
-                          cudaStream_t s) {
+                          const void* tensor_maps, cudaStream_t s) {
+  CUtensorMap tmT;
+  memcpy(&tmT, tensor_maps, sizeof(CUtensorMap));  // the arrival-time plane's map (flood_make_tensor_maps)
   cudaError_t e = cudaMemsetAsync(ndistinct, 0, sizeof(uint32_t) * (size_t)d.n_img, s);
   if (e != cudaSuccess) return e;
   // the pending slots of halo rows this plan does not have read as resolved (bit 31 set) to whoever counts them
   e = cudaMemsetAsync(b.rim + (size_t)d.tiles_total() * RIM_PER_TILE, 0x80, 2 * (size_t)d.cols * sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  if (tie_random) label_tile_kernel<true><<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d, ndistinct, tie_seed);
-  else label_tile_kernel<false><<<d.tiles_total(), LT_THREADS, 0, s>>>(b, d, ndistinct, 0ull);
+  if (tie_random) label_tile_kernel<true><<<d.tiles_total(), LT_THREADS, 0, s>>>(tmT, b, d, ndistinct, tie_seed);
+  else label_tile_kernel<false><<<d.tiles_total(), LT_THREADS, 0, s>>>(tmT, b, d, ndistinct, 0ull);
   return cudaGetLastError();
 }
 
