@@ -28,6 +28,9 @@
 
 #include <cstring>
 
+#ifndef WS_FLOOD_MINCTAS
+#define WS_FLOOD_MINCTAS 3   // co-resident CTAs per SM the register budget is set for
+#endif
 #ifndef WS_FLOOD_BULK
 #define WS_FLOOD_BULK 3
 #endif
@@ -747,7 +750,7 @@ __device__ __forceinline__ int flood_pop(const FloodBuffers& b, int lane, uint32
 }
 
 // Persistent kernel, no grid barrier.  See the head of this file.
-__global__ void __launch_bounds__(FLOOD_THREADS, 3) flood_kernel(const __grid_constant__ FloodArgs a) {
+__global__ void __launch_bounds__(FLOOD_THREADS, WS_FLOOD_MINCTAS) flood_kernel(const __grid_constant__ FloodArgs a) {
   __shared__ FloodSmem sm;
   const ImageDims& d = a.d;
   const bool producer = threadIdx.x >= FLOOD_CONSUMERS;
