@@ -95,7 +95,31 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
   // node i = tid + 256 k sits at (row, column) = (i / 65, i % 65): 256 = 3 * 65 + 61, so no division per node
   static_assert(MR_THREADS == 3 * MR_NW + 61, "incremental node coordinates");
   const int nr0 = tid / MR_NW, nc0 = tid - nr0 * MR_NW;
-  {
+  // the node grid lies inside the image (all tiles but those of the last tile row / column): no bounds tests,
+  // offsets by addition
+  const bool whole = r0 + MR_NH <= d.rows && c0 + MR_NW <= d.cols;
+  if (whole) {
+    const size_t p0 = base + (size_t)(r0 + nr0) * d.cols + c0 + nc0;
+    const uint32_t* lp = lab + p0;
+    const uint8_t* vp = lvl + p0;
+    // node + 256 = 3 rows down and 61 right, or 4 down and 4 left (unsigned: up to 36 rows of a very wide image)
+    const uint32_t step3 = 3u * (uint32_t)d.cols + 61u, back = (uint32_t)d.cols - (uint32_t)MR_NW;
+    int c = nc0;
+    uint32_t off = 0;
+#pragma unroll
+    for (int k = 0; k < MR_PER_THREAD; ++k) {
+      const int i = tid + k * MR_THREADS;
+      L[k] = 0;
+      V[k] = 255;
+      if (i < MR_NODES) {
+        L[k] = __ldg(lp + off);
+        V[k] = __ldg(vp + off);
+      }
+      off += step3;
+      c += 61;
+      if (c >= MR_NW) { c -= MR_NW; off += back; }
+    }
+  } else {
     int r = nr0, c = nc0;
 #pragma unroll
     for (int k = 0; k < MR_PER_THREAD; ++k) {
@@ -198,6 +222,8 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
   const int nlab = (int)sm.nlab;
   if (nlab > Z::MAXN || sm.overflow) return false;   // (uniform: both were written before the barrier)
   int nr = nr0, nc = nc0;
+  const bool all_open = !contract, strip = d.halo_top || d.halo_bottom;
+  const int rim_r = r0 > 0 ? 0 : -1, rim_c = c0 > 0 ? 0 : -1;   // first row / column, when a tile lies beyond it
 #pragma unroll
   for (int k = 0; k < MR_PER_THREAD; ++k, nr += 3, nc += 61) {
     if (nc >= MR_NW) { nc -= MR_NW; ++nr; }   // (row, column) of node tid + 256 k
@@ -210,10 +236,12 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
       // rim: pixels whose up / left neighbour lies outside the tile, and the neighbour row / column itself;
       // in a row strip also the halo rows (the neighbouring strip's pixels) and the first owned row below a
       // halo (its upward edges belong to the neighbouring strip)
-      const int gr = r0 + r;
-      if (!contract || r == TILE_H || c == TILE_W || (r == 0 && r0 > 0) || (c == 0 && c0 > 0) ||
-          (d.halo_top && gr <= 1) || (d.halo_bottom && gr == d.rows - 1))
-        sm.open_[id] = 1;
+      bool rim = all_open || r == TILE_H || c == TILE_W || r == rim_r || c == rim_c;
+      if (strip) {
+        const int gr = r0 + r;
+        rim = rim || (d.halo_top && gr <= 1) || (d.halo_bottom && gr == d.rows - 1);
+      }
+      if (rim) sm.open_[id] = 1;
     }
     sm.b.n.node[i] |= id;  // (MR_NOLAB = 0xFFFF for uncoloured nodes)
   }
