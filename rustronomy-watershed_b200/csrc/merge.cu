@@ -70,6 +70,29 @@ struct MergeSmem {
   uint32_t nlab, nout, gpos, first, overflow;
 };
 
+// The right / down edges of a pixel of a tile on the image's border or of a row strip (one copy of the code for
+// the eight pixels of a thread: these tiles are few, the kernel is short of instruction cache).
+__device__ __noinline__ uint2 mr_border_edges(int gr, int gc, int rows, int cols, int row_offset, int global_rows,
+                                              int halos, uint32_t na, uint32_t nr, uint32_t nd) {
+  const uint32_t a = na & 0xFFFFu, br = nr & 0xFFFFu, bd = nd & 0xFFFFu;
+  uint2 e = make_uint2(MR_NONE, MR_NONE);  // (right, down)
+  // window centres of the WHOLE field (lib.rs:220, 411-414), in local coordinates: ImageDims::is_centre
+  auto centre = [&](int r, int c) {
+    const int g = r + row_offset;
+    return g >= 1 && g <= global_rows - 2 && c >= 1 && c <= cols - 2;
+  };
+  // An edge belongs to the strip that owns its upper / left pixel; a halo row's own edges are the
+  // neighbouring strip's.  Plain plans own every row.  (halos: bit 0 = halo_top, bit 1 = halo_bottom)
+  if (a != MR_NOLAB && gr < rows && !((halos & 1) && gr == 0) && !((halos & 2) && gr == rows - 1)) {
+    const bool pin = centre(gr, gc);
+    if (br != MR_NOLAB && br != a && (pin || centre(gr, gc + 1)))
+      e.x = a | (br << 12) | (max(na >> 16, nr >> 16) << 24);
+    if (bd != MR_NOLAB && bd != a && (pin || centre(gr + 1, gc)))
+      e.y = a | (bd << 12) | (max(na >> 16, nd >> 16) << 24);
+  }
+  return e;
+}
+
 // One Boruvka over the tile's basin graph; every component picks its lightest edge in every round.  A pick
 // made by a component that holds closed basins only is FINAL (cut property: all edges of a closed basin lie
 // in this tile), every other pick is DEFERRED.  `contract` = 0 treats every basin as open (no FINAL edges).
@@ -177,6 +200,8 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
     uint32_t h = (l * 2654435761u) >> Z::HSHIFT;
     if (lead && l != 0u) {
       int probes = 0;
+#pragma unroll 1   // (unrolled four times in each of the nine copies it was a quarter of the kernel's code: the
+                   //  kernel's top stall reason was instruction fetch)
       for (;; ++probes) {
         if (probes == Z::HASH) {   // more distinct labels than slots (small size only)
           sm.overflow = 1;
@@ -268,16 +293,10 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
         if (bd != MR_NOLAB && bd != a) ed = a | (bd << 12) | (max(na >> 16, nd >> 16) << 24);
       }
     } else {
-      const int gr = r0 + r, gc = c0 + lc;
-      // An edge belongs to the strip that owns its upper / left pixel; a halo row's own edges are the
-      // neighbouring strip's.  Plain plans own every row.
-      if (a != MR_NOLAB && gr < d.rows && !(d.halo_top && gr == 0) && !(d.halo_bottom && gr == d.rows - 1)) {
-        const bool pin = d.is_centre(gr, gc);
-        if (br != MR_NOLAB && br != a && (pin || d.is_centre(gr, gc + 1)))
-          er = a | (br << 12) | (max(na >> 16, nr >> 16) << 24);
-        if (bd != MR_NOLAB && bd != a && (pin || d.is_centre(gr + 1, gc)))
-          ed = a | (bd << 12) | (max(na >> 16, nd >> 16) << 24);
-      }
+      const uint2 e = mr_border_edges(r0 + r, c0 + lc, d.rows, d.cols, d.row_offset, d.global_rows,
+                                      (d.halo_top ? 1 : 0) | (d.halo_bottom ? 2 : 0), na, nr, nd);
+      er = e.x;
+      ed = e.y;
     }
     // (no write of this loop can hit the table's last readers: they are behind the barrier above)
     uint32_t m = __ballot_sync(0xffffffffu, er != MR_NONE);
@@ -293,6 +312,7 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
   if (!__syncthreads_or(cnt != 0u)) return true;  // no edge between different basins in this tile
   if (sm.overflow) return false;                  // (written before the barrier: uniform)
   // (node[] is dead from here on: its memory becomes best / comp / link)
+#pragma unroll 1
   for (int i = tid; i < nlab; i += MR_THREADS) {
     sm.b.r.best[i] = MR_NONE;
     sm.b.r.comp[i] = (uint16_t)i;
@@ -320,6 +340,7 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
     if (lane == 0) atomicAdd(&red_count[6], cnt);
 #endif
     // every picking root goes under the component at the other end of its edge
+#pragma unroll 1
     for (int i = tid; i < nlab; i += MR_THREADS) {
       if (sm.b.r.comp[i] != (uint16_t)i) continue;
       const uint32_t key = sm.b.r.best[i];
@@ -338,6 +359,7 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
     __syncthreads();
     // roots (reads racing with the flattening stores still see an ancestor).  An id that was a root and has
     // just gone under another component keeps the edge it went along (the list is not compacted in between).
+#pragma unroll 1
     for (int i = tid; i < nlab; i += MR_THREADS) {
       uint32_t x = (uint32_t)i;
       for (uint32_t p = sm.parent[x]; p != x; p = sm.parent[x]) x = p;
@@ -383,6 +405,7 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
   // themselves, DEFERRED ones between the identities of the two basins (the end of their chains of FINAL moves)
   uint32_t mine = 0;
   if (tid == 0) sm.first = 0;  // from here on: cursor into this tile's part of the global list
+#pragma unroll 1
   for (int i = tid; i < nlab; i += MR_THREADS) mine += (sm.parent[i] != (uint16_t)i);
   if (mine) atomicAdd(&sm.nout, mine);
   __syncthreads();
@@ -395,6 +418,7 @@ __device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, con
   __syncthreads();
   const uint32_t gbase = __ldg(seed_off + img) - 1u;  // global colour id = seed_off[img] + colour - 1
   uint32_t at = mine ? sm.gpos + atomicAdd(&sm.first, mine) : 0u;
+#pragma unroll 1
   for (int i = tid; i < nlab; i += MR_THREADS) {
     if (sm.parent[i] == (uint16_t)i) continue;
     const uint32_t e = sm.b.r.best[i];
