@@ -532,8 +532,10 @@ def main():
                 # the same launch against the hardware instead of against the reference's 255 passes:
                 "dram_gbs": (traffic / (flood_avg_ms * 1e-3) / 1e9) if traffic else None,
                 "one_pass_bytes": one_pass, "one_pass_frac": one_pass / (flood_avg_ms * 1e-3) / 1e9 / peak,
-                "limiter": "issue rate of the in-tile relaxation (ncu: issue slots 66 % busy, 2.7 G warp instructions, "
-                           "consumer warps wait 4 % for staged tiles); see profiles/r01_k_flood_kernel_*",
+                "limiter": "issue rate of the in-tile relaxation (ncu, stage r02_n: issue slots 58 % busy, 1.94 G warp "
+                           "instructions, 2.03 activations per tile); consumer warps waited "
+                           f"{100.0 * stats['flood_wait_kcycles'] / max(1, stats['flood_wait_kcycles'] + stats['flood_busy_kcycles']):.0f} % "
+                           "of this run for staged tiles (live counter); see " + str(kt.get("flood", {}).get("file")),
                 "note": "algorithmic bytes = 9 B x pixels x 255 levels (one streaming pass per level, SURVEY 8(d)); "
                         "the kernel computes all levels in ONE arrival-time propagation, so frac > 1 is expected; "
                         "traffic = measured DRAM bytes per launch (ncu), see profiles/; one_pass_* = the bound of "
