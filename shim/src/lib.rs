@@ -21,6 +21,8 @@
 compile_error!("the engine's labels are 64-bit: usize must be u64");
 
 pub mod ffi;
+#[cfg(feature = "plots")]
+pub mod plotting;
 
 use ndarray as nd;
 use num_traits::{Num, ToPrimitive};
@@ -35,6 +37,34 @@ pub const NEVER_FILL: u8 = u8::MAX;
 /// lib.rs:144-154
 pub mod prelude {
   pub use crate::{MergingWatershed, TransformBuilder, Watershed, WatershedUtils};
+  #[cfg(feature = "plots")]
+  pub mod color_maps {
+    pub use crate::plotting::{grey_scale, inferno, magma, plasma, viridis};
+  }
+}
+
+/// `fn(count, min, max)` of the `plots` feature (lib.rs:913-916)
+#[cfg(feature = "plots")]
+pub type ColourMap = fn(usize, usize, usize) -> Result<plotting::RGBColor, Box<dyn std::error::Error>>;
+
+/// The two options of the `plots` feature (lib.rs:910-916, 1299-1304); empty without it.
+#[derive(Clone)]
+struct PlotCfg {
+  #[cfg(feature = "plots")]
+  path: Option<std::path::PathBuf>,
+  #[cfg(feature = "plots")]
+  map: Option<ColourMap>,
+}
+
+impl PlotCfg {
+  const fn none() -> Self {
+    PlotCfg {
+      #[cfg(feature = "plots")]
+      path: None,
+      #[cfg(feature = "plots")]
+      map: None,
+    }
+  }
 }
 
 ////////////////////////////////////////////////////////////////////////////////
@@ -111,7 +141,7 @@ pub struct HookCtx<'a> {
   pub seeds: &'a [(usize, (usize, usize))],
 }
 
-/// lib.rs:908-1047 (the `plots` options are out of scope of the engine)
+/// lib.rs:908-1047, with the two options of the `plots` feature (lib.rs:972-994) behind the same feature gate
 #[derive(Clone)]
 pub struct TransformBuilder<T = ()> {
   max_water_level: u8,
@@ -119,6 +149,7 @@ pub struct TransformBuilder<T = ()> {
   wlvl_hook: Option<fn(HookCtx) -> T>,
   tie_break: u8,
   tie_seed: Option<u64>,
+  plots: PlotCfg,
 }
 
 impl Default for TransformBuilder<()> {
@@ -135,7 +166,22 @@ impl<T> TransformBuilder<T> {
       wlvl_hook: None,
       tie_break: ffi::WS_TIE_FIRST,
       tie_seed: None,
+      plots: PlotCfg::none(),
     }
+  }
+
+  /// lib.rs:975-985
+  #[cfg(feature = "plots")]
+  pub const fn set_plot_colour_map(mut self, colour_map: ColourMap) -> Self {
+    self.plots.map = Some(colour_map);
+    self
+  }
+
+  /// lib.rs:991-994: with a folder set, every water level writes `ws_lvl{level}.png` there
+  #[cfg(feature = "plots")]
+  pub fn set_plot_folder(mut self, path: &std::path::Path) -> Self {
+    self.plots.path = Some(path.to_path_buf());
+    self
   }
 
   pub const fn set_max_water_lvl(mut self, max_water_lvl: u8) -> Self {
@@ -183,6 +229,7 @@ impl<T> TransformBuilder<T> {
       wlvl_hook: self.wlvl_hook,
       tie_break: self.tie_break,
       tie_seed: self.tie_seed,
+      plots: self.plots,
     })
   }
 
@@ -194,6 +241,7 @@ impl<T> TransformBuilder<T> {
       wlvl_hook: self.wlvl_hook,
       tie_break: self.tie_break,
       tie_seed: self.tie_seed,
+      plots: self.plots,
     })
   }
 }
@@ -299,6 +347,7 @@ pub struct MergingWatershed<T = ()> {
   wlvl_hook: Option<fn(HookCtx) -> T>,
   tie_break: u8,
   tie_seed: Option<u64>,
+  plots: PlotCfg,
 }
 
 /// lib.rs:1609-1617
@@ -309,15 +358,55 @@ pub struct SegmentingWatershed<T = ()> {
   wlvl_hook: Option<fn(HookCtx) -> T>,
   tie_break: u8,
   tie_seed: Option<u64>,
+  plots: PlotCfg,
 }
 
 /// What both transforms share: the configuration that reaches the engine and the four entry points.
 struct Engine {
   cfg: ffi::ws_config,
   tie_seed: Option<u64>,
+  plots: PlotCfg,
 }
 
 impl Engine {
+  #[cfg(feature = "plots")]
+  fn has_plots(&self) -> bool {
+    self.plots.path.is_some()
+  }
+  #[cfg(not(feature = "plots"))]
+  fn has_plots(&self) -> bool {
+    false
+  }
+
+  /// lib.rs:1472-1487 / 1758-1773: the level's label image without the edge-correction padding; a plot that
+  /// fails is reported and the transform goes on.
+  #[cfg(feature = "plots")]
+  fn draw(&self, ctx: &HookCtx) {
+    if let Some(path) = &self.plots.path {
+      let shape = ctx.colours.shape();
+      let picture = if self.cfg.edge_correction != 0 {
+        ctx.colours.slice(nd::s![1..(shape[0] - 1), 1..(shape[1] - 1)])
+      } else {
+        ctx.colours.view()
+      };
+      let map: ColourMap = self.plots.map.unwrap_or(plotting::viridis::<usize>); // lib.rs:1011
+      if let Err(err) = plotting::plot_slice(picture, &path.join(format!("ws_lvl{}.png", ctx.water_level)), map) {
+        println!("Could not make watershed plot. Error: {err}")
+      }
+    }
+  }
+  #[cfg(not(feature = "plots"))]
+  fn draw(&self, _ctx: &HookCtx) {}
+
+  /// The reference routes `transform`, `transform_history` and `transform_to_list` through
+  /// `transform_with_hook` (lib.rs:1524-1560), so they plot too; here they have device paths of their own, and
+  /// with a plot folder set one extra pass through the per-level hook makes the pictures.
+  fn plot_pass(&self, input: nd::ArrayView2<u8>, seeds: &[(usize, usize)]) {
+    if self.has_plots() {
+      self.with_hook(input, seeds, |ctx: HookCtx| self.draw(&ctx));
+    }
+  }
+
   fn prepare(&self, ctx: *mut ffi::ws_ctx) {
     if let (ffi::WS_TIE_RANDOM, Some(seed)) = (self.cfg.tie_break, self.tie_seed) {
       check(ctx, unsafe { ffi::ws_ctx_set_tie_seed(ctx, seed) });
@@ -326,6 +415,7 @@ impl Engine {
 
   /// Watershed::transform
   fn transform(&self, input: nd::ArrayView2<u8>, seeds: &[(usize, usize)]) -> nd::Array2<usize> {
+    self.plot_pass(input.view(), seeds);
     // merging: the input shape (lib.rs:1524-1536); segmenting: the padded shape
     let shape = if self.cfg.kind == ffi::WS_MERGING { (input.nrows(), input.ncols()) } else { out_shape(self.cfg.edge_correction != 0, &input) };
     let mut out = nd::Array2::<usize>::zeros(shape);
@@ -389,7 +479,10 @@ impl Engine {
   /// Watershed::transform_history (lib.rs:1538-1549 / 1824-1835): `(level, colours.to_owned())` per level --
   /// every snapshot is copied once, out of the engine's page-locked buffer into its own Array2.
   fn history(&self, input: nd::ArrayView2<u8>, seeds: &[(usize, usize)]) -> Vec<(u8, nd::Array2<usize>)> {
-    self.with_hook(input, seeds, |ctx: HookCtx| (ctx.water_level, ctx.colours.to_owned()))
+    self.with_hook(input, seeds, |ctx: HookCtx| {
+      self.draw(&ctx);
+      (ctx.water_level, ctx.colours.to_owned())
+    })
   }
 
   /// Watershed::transform_to_list (lib.rs:1551-1561 / 1837-1847): `(level, find_lake_sizes(colours))` per level.
@@ -407,6 +500,7 @@ impl Engine {
         out_sizes: *mut u64,
       ) -> c_int;
     }
+    self.plot_pass(input.view(), seeds);
     let (r, c) = out_shape(self.cfg.edge_correction != 0, &input);
     let levels = self.cfg.max_water_level as usize + 1;
     let ncol = seeds.len() + 1;
@@ -443,6 +537,7 @@ macro_rules! impl_watershed {
             tie_break: self.tie_break,
           },
           tie_seed: self.tie_seed,
+          plots: self.plots.clone(),
         }
       }
     }
@@ -453,9 +548,18 @@ macro_rules! impl_watershed {
       }
 
       fn transform_with_hook(&self, input: nd::ArrayView2<u8>, seeds: &[(usize, usize)]) -> Vec<T> {
+        let engine = self.engine();
         match self.wlvl_hook {
-          Some(hook) => self.engine().with_hook(input, seeds, hook),
-          None => Vec::new(), // lib.rs:1510, 1520 / 1796, 1806: no hook, no results (the flood is not needed then)
+          Some(hook) if engine.has_plots() => engine.with_hook(input, seeds, |ctx: HookCtx| {
+            engine.draw(&ctx);
+            hook(ctx)
+          }),
+          Some(hook) => engine.with_hook(input, seeds, hook),
+          None => {
+            // lib.rs:1510, 1520 / 1796, 1806: no hook, no results (without a plot folder the flood is not needed)
+            engine.plot_pass(input, seeds);
+            Vec::new()
+          }
         }
       }
 
