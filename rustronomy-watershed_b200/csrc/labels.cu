@@ -57,7 +57,6 @@ struct __align__(128) LabelSmem {
   uint64_t bar;
   uint32_t rb[2 * TILE_H];        // sorted seed lists: rowbase of the tile's rows, one word per 32 columns
   uint32_t nseed_px;
-  int img, ty, tx;
 };
 
 // counter-based generator of the random tie-break: splitmix64 of (key, position of the pixel in the field)
@@ -169,10 +168,21 @@ __global__ void __launch_bounds__(LT_THREADS, 6) label_tile_kernel(const __grid_
                                                                    uint64_t tie_seed) {
   __shared__ LabelSmem sm;
   const int tid = threadIdx.x;
-  const int tpi = d.tiles_per_img();
-  const int img = blockIdx.x / tpi;
-  const int trem = blockIdx.x - img * tpi;
-  const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
+  // grid = (tiles_x, tiles_y, slices) whenever that fits a grid (launch_parent): no divisions at the head of the CTA,
+  // where they sat in front of the tile's copy
+  int img, ty, tx;
+  if (gridDim.y * gridDim.z > 1u || d.tiles_y * d.n_img == 1) {
+    tx = (int)blockIdx.x;
+    ty = (int)blockIdx.y;
+    img = (int)blockIdx.z;
+  } else {
+    const int tpi = d.tiles_per_img();
+    img = (int)blockIdx.x / tpi;
+    const int trem = (int)blockIdx.x - img * tpi;
+    ty = trem / d.tiles_x;
+    tx = trem - ty * d.tiles_x;
+  }
+  const int tile = (img * d.tiles_y + ty) * d.tiles_x + tx;
   const int r0 = ty * TILE_H, c0 = tx * TILE_W;
   if (tid == 0) {
     // box rows r0-1 .. r0+32 (padded row index r0 .. r0+33), columns c0-4 .. c0+67; the flood's results were
@@ -198,12 +208,13 @@ __global__ void __launch_bounds__(LT_THREADS, 6) label_tile_kernel(const __grid_
   const size_t base = (size_t)img * d.px_per_img();
   const bool plain = r0 + TILE_H <= d.rows && c0 + TILE_W <= d.cols && !(d.halo_top && ty == 0) &&
                      !(d.halo_bottom && r0 + TILE_H >= d.rows);
+  // (loaded by every thread and used late: behind a barrier the load's latency was on every CTA's critical path)
   const uint32_t col_first = b.colour_base + 1u - __ldg(b.seed_off + img);   // colour of the slice's seed 0, minus its index
   mbar_wait(&sm.bar, 0);
 
   uint32_t nseed_warp;
-  if (plain) nseed_warp = lt_parents<kTieRandom, true>(sm, b, d, img, r0, c0, blockIdx.x, sorted, col_first, tie_seed);
-  else nseed_warp = lt_parents<kTieRandom, false>(sm, b, d, img, r0, c0, blockIdx.x, sorted, col_first, tie_seed);
+  if (plain) nseed_warp = lt_parents<kTieRandom, true>(sm, b, d, img, r0, c0, tile, sorted, col_first, tie_seed);
+  else nseed_warp = lt_parents<kTieRandom, false>(sm, b, d, img, r0, c0, tile, sorted, col_first, tie_seed);
   // (a later duplicate seed overwrites an earlier one, lib.rs:1365-1367, so a pixel counts once)
   if ((tid & 31) == 0 && nseed_warp) atomicAdd(&sm.nseed_px, nseed_warp);
   __syncthreads();
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(LT_THREADS, 6) label_tile_kernel(const __grid_
     else if (tid < 2 * TILE_W + TILE_H - 2) { lr = 1 + (tid - 2 * TILE_W); lcc = 0; }
     else { lr = 1 + (tid - 2 * TILE_W - (TILE_H - 2)); lcc = TILE_W - 1; }
     const bool in = (r0 + lr < d.rows) && (c0 + lcc < d.cols);
-    __stcg(b.rim + (size_t)blockIdx.x * RIM_PER_TILE + tid, in ? sm.w[lr * TILE_W + lcc] : LAB_RESOLVED);
+    __stcg(b.rim + (size_t)tile * RIM_PER_TILE + tid, in ? sm.w[lr * TILE_W + lcc] : LAB_RESOLVED);
   }
 }
 
@@ -266,8 +277,9 @@ cudaError_t launch_parent(FloodBuffers b, ImageDims d, uint32_t* ndistinct, bool
   // the pending slots of halo rows this plan does not have read as resolved (bit 31 set) to whoever counts them
   e = cudaMemsetAsync(b.rim + (size_t)d.tiles_total() * RIM_PER_TILE, 0x80, 2 * (size_t)d.cols * sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  if (tie_random) label_tile_kernel<true><<<d.tiles_total(), LT_THREADS, 0, s>>>(tmT, b, d, ndistinct, tie_seed);
-  else label_tile_kernel<false><<<d.tiles_total(), LT_THREADS, 0, s>>>(tmT, b, d, ndistinct, 0ull);
+  const dim3 grid = (d.tiles_y <= 65535 && d.n_img <= 65535) ? dim3(d.tiles_x, d.tiles_y, d.n_img) : dim3(d.tiles_total());
+  if (tie_random) label_tile_kernel<true><<<grid, LT_THREADS, 0, s>>>(tmT, b, d, ndistinct, tie_seed);
+  else label_tile_kernel<false><<<grid, LT_THREADS, 0, s>>>(tmT, b, d, ndistinct, 0ull);
   return cudaGetLastError();
 }
 

@@ -98,16 +98,13 @@ __device__ __noinline__ uint2 mr_border_edges(int gr, int gc, int rows, int cols
 // in this tile), every other pick is DEFERRED.  `contract` = 0 treats every basin as open (no FINAL edges).
 // Returns false when the tile does not fit this size (nothing has been emitted then).
 template <typename Z>
-__device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int tile, const uint32_t* __restrict__ lab,
+__device__ __forceinline__ bool merge_tile(MergeSmem<Z>& sm, const int img, const int ty, const int tx,
+                                           const uint32_t* __restrict__ lab,
                                            const uint8_t* __restrict__ lvl, const ImageDims& d,
                                            const uint32_t* __restrict__ seed_off, const int contract,
                                            uint2* __restrict__ red_ab, uint8_t* __restrict__ red_w,
                                            uint32_t* __restrict__ red_count) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tpi = d.tiles_per_img();
-  const int img = tile / tpi;
-  const int trem = tile - img * tpi;
-  const int ty = trem / d.tiles_x, tx = trem - ty * d.tiles_x;
   const int r0 = ty * TILE_H, c0 = tx * TILE_W;
   const size_t base = (size_t)img * d.px_per_img();
 
@@ -445,9 +442,22 @@ __global__ void __launch_bounds__(MR_THREADS, 6) merge_reduce_kernel(const uint3
                                                                      uint32_t* __restrict__ red_count,
                                                                      uint32_t* __restrict__ ovf_list) {
   __shared__ MergeSmem<MrSmall> sm;
-  if (!merge_tile<MrSmall>(sm, (int)blockIdx.x, lab, lvl, d, seed_off, contract, red_ab, red_w, red_count) &&
+  // grid = (tiles_x, tiles_y, slices) whenever that fits a grid: no divisions per thread
+  int img, ty, tx;
+  if (gridDim.y * gridDim.z > 1u || d.tiles_y * d.n_img == 1) {
+    tx = (int)blockIdx.x;
+    ty = (int)blockIdx.y;
+    img = (int)blockIdx.z;
+  } else {
+    const int tpi = d.tiles_per_img();
+    img = (int)blockIdx.x / tpi;
+    const int trem = (int)blockIdx.x - img * tpi;
+    ty = trem / d.tiles_x;
+    tx = trem - ty * d.tiles_x;
+  }
+  if (!merge_tile<MrSmall>(sm, img, ty, tx, lab, lvl, d, seed_off, contract, red_ab, red_w, red_count) &&
       threadIdx.x == 0)
-    ovf_list[atomicAdd(&red_count[12], 1u)] = blockIdx.x;
+    ovf_list[atomicAdd(&red_count[12], 1u)] = (uint32_t)((img * d.tiles_y + ty) * d.tiles_x + tx);
 }
 
 // the listed tiles with the full size (a persistent grid: the list is usually empty)
@@ -460,7 +470,9 @@ __global__ void __launch_bounds__(MR_THREADS) merge_reduce_full_kernel(const uin
   __shared__ MergeSmem<MrFull> sm;
   const uint32_t n = red_count[12];
   for (uint32_t k = blockIdx.x; k < n; k += gridDim.x) {
-    merge_tile<MrFull>(sm, (int)ovf_list[k], lab, lvl, d, seed_off, contract, red_ab, red_w, red_count);
+    const int tile = (int)ovf_list[k], tpi = d.tiles_per_img();
+    const int img = tile / tpi, trem = tile - img * tpi;
+    merge_tile<MrFull>(sm, img, trem / d.tiles_x, trem % d.tiles_x, lab, lvl, d, seed_off, contract, red_ab, red_w, red_count);
     __syncthreads();  // the next tile reuses the shared memory
   }
 }
@@ -472,8 +484,8 @@ cudaError_t launch_merge_reduce(const uint32_t* lab, const uint8_t* lvl, ImageDi
                                 cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(red_count, 0, 16 * sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  merge_reduce_kernel<<<d.tiles_total(), MR_THREADS, 0, s>>>(lab, lvl, d, seed_off, contract, red_ab, red_w, red_count,
-                                                               ovf_list);
+  const dim3 grid = (d.tiles_y <= 65535 && d.n_img <= 65535) ? dim3(d.tiles_x, d.tiles_y, d.n_img) : dim3(d.tiles_total());
+  merge_reduce_kernel<<<grid, MR_THREADS, 0, s>>>(lab, lvl, d, seed_off, contract, red_ab, red_w, red_count, ovf_list);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int want = d.tiles_total(), cap = num_sms() * 4;
