@@ -1169,8 +1169,19 @@ struct Trace {
 };
 
 // ---- staged copies between pageable caller memory and the device (hostpipe.h) --------------------------
-constexpr size_t RING_SLOT_BYTES = (size_t)32 << 20;
-constexpr int RING_SLOTS = 4;
+// Ring geometry, measured on the pool's hosts (one 16384^2 segmenting transform into pageable usize labels, medians;
+// scripts/hostbench/e2e_ab.py): 4 x 32 MB 50 ms, 4 x 16 MB 46 ms, 4 x 8 MB 44 ms, 6 x 8 MB 35.8 ms, 8 x 8 MB 35.5 ms,
+// 8 x 4 MB 42 ms, 8 x 16 MB 43 ms.  The device -> host direction keeps RING_SLOTS - 1 copies queued ahead of the
+// workers: with three of them the link idled between a slot's arrival and the next copy's start; slots below
+// 8 MB pay for the hand-over to the worker threads (one wake-up and join per slot).
+#ifndef WS_RING_SLOT_MB
+#define WS_RING_SLOT_MB 8
+#endif
+constexpr size_t RING_SLOT_BYTES = (size_t)WS_RING_SLOT_MB << 20;
+#ifndef WS_RING_SLOTS
+#define WS_RING_SLOTS 8
+#endif
+constexpr int RING_SLOTS = WS_RING_SLOTS;   // (at most 8: ws_ctx::ring_ev)
 
 ws_status ensure_ring(ws_ctx* ctx) {
   if (!ctx->host_threads) {
