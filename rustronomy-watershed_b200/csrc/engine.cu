@@ -780,6 +780,22 @@ extern "C" ws_status ws_plan_snapshot(ws_plan* p, ws_kind kind, size_t i, uint8_
   return WS_OK;
 }
 
+// the snapshot of slice 0 as 32-bit words (internal: the pageable history / hook paths)
+static ws_status plan_snapshot32(ws_plan* p, ws_kind kind, uint8_t level, uint32_t* d_out) {
+  ws_ctx* ctx = p->ctx;
+  const size_t n = p->d.px_per_img();
+  const uint32_t* rep = nullptr;
+  uint32_t base = 0;
+  if (kind == WS_MERGING) {
+    WS_TRY(plan_rep_table(p, level));
+    rep = p->rep;
+    base = !p->h_seed_off.empty() ? p->h_seed_off[0] : 0;
+  }
+  WS_CUDA(ctx, launch_snapshot32(p->fb.lab, p->fb.lvl, n, level, rep, base, d_out, ctx->stream));
+  p->stats[4] += 1;
+  return WS_OK;
+}
+
 // ---------------------------------------------------------------------------
 // row-strip decomposition of one field over several plans / GPUs
 // ---------------------------------------------------------------------------
@@ -1472,8 +1488,7 @@ ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint6
   const size_t npx = hr.npx;
   const uint32_t nlev = (uint32_t)cfg->max_water_level + 1u;
   // Caller memory that is page-locked takes the copies directly.  Pageable memory would make the driver
-  // stage every copy itself (~20 GB/s measured): go through our own pinned double buffer instead and move
-  // level l - 1 out with several host threads while level l crosses the link.
+  // stage every copy itself (~20 GB/s measured): it goes through the ring and the worker threads instead.
   bool staged = true;
   if (direct) {
     cudaPointerAttributes at;
@@ -1482,7 +1497,7 @@ ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint6
   }
   for (int i = 0; i < 2; ++i) {
     WS_TRY(grow(ctx, ctx->d_out[i], ctx->d_out_cap[i], npx));
-    if (staged && ctx->h_pin_cap[i] < npx) {
+    if (staged && !direct && i == 0 && ctx->h_pin_cap[i] < npx) {
       if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
       ctx->h_pin[i] = nullptr; ctx->h_pin_cap[i] = 0;
       WS_CUDA(ctx, cudaMallocHost((void**)&ctx->h_pin[i], npx * 8));
@@ -1490,23 +1505,32 @@ ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint6
     }
   }
   const ws_kind kind = (ws_kind)cfg->kind;
-  for (uint32_t l = 0; l <= nlev; ++l) {
+  if (staged) {
+    // Pageable destination (an ordinary Vec<Array2<usize>>) or a hook: the snapshots cross the link as 32-bit words
+    // through the ring and the workers widen them into place (the caller's array, or one page-locked image for the
+    // hook) -- 4 B per pixel on the link and 12 B of host traffic instead of 8 and 24.  Level l + 1 is cut while
+    // level l is on its way.
+    WS_TRY(plan_snapshot32(p, kind, 0, reinterpret_cast<uint32_t*>(ctx->d_out[0])));
+    for (uint32_t l = 0; l < nlev; ++l) {
+      const int buf = l & 1;
+      if (l + 1 < nlev) WS_TRY(plan_snapshot32(p, kind, (uint8_t)(l + 1), reinterpret_cast<uint32_t*>(ctx->d_out[buf ^ 1])));
+      uint64_t* dst = direct ? direct + (size_t)l * npx : ctx->h_pin[0];
+      WS_TRY(staged_d2h(ctx, ctx->d_out[buf], npx * 4, [=](const uint8_t* sp, size_t off, size_t len) {
+        widen_labels_host(dst + off / 4, reinterpret_cast<const uint32_t*>(sp), len / 4);
+      }));
+      if (!direct) sink((uint8_t)l, ctx->h_pin[0]);
+    }
+    WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return WS_OK;
+  }
+  for (uint32_t l = 0; l < nlev; ++l) {  // page-locked destination: straight over the link, two levels in flight
     const int buf = l & 1;
-    if (l < nlev) {
-      if (l >= 2) WS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
-      WS_TRY(ws_plan_snapshot(p, kind, 0, (uint8_t)l, ctx->d_out[buf]));
-      WS_CUDA(ctx, cudaEventRecord(ctx->ev_ready[buf], ctx->stream));
-      WS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[buf], 0));
-      uint64_t* dst = staged ? ctx->h_pin[buf] : direct + (size_t)l * npx;
-      WS_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_out[buf], npx * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
-      WS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
-    }
-    if (l >= 1 && staged) {  // hand level l-1 on while level l is in flight
-      const int pb = (l - 1) & 1;
-      WS_CUDA(ctx, cudaEventSynchronize(ctx->ev_copied[pb]));
-      if (direct) parallel_memcpy(direct + (size_t)(l - 1) * npx, ctx->h_pin[pb], npx * 8);
-      else sink((uint8_t)(l - 1), ctx->h_pin[pb]);
-    }
+    if (l >= 2) WS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[buf], 0));
+    WS_TRY(ws_plan_snapshot(p, kind, 0, (uint8_t)l, ctx->d_out[buf]));
+    WS_CUDA(ctx, cudaEventRecord(ctx->ev_ready[buf], ctx->stream));
+    WS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[buf], 0));
+    WS_CUDA(ctx, cudaMemcpyAsync(direct + (size_t)l * npx, ctx->d_out[buf], npx * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    WS_CUDA(ctx, cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
   }
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   WS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

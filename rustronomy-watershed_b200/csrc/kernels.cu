@@ -480,10 +480,11 @@ cudaError_t launch_rep_table(const uint32_t* hook_to, const uint8_t* hook_lvl, u
 // K5-K7  per-level outputs
 // ===========================================================================
 
+template <typename O>
 __global__ void __launch_bounds__(256) snapshot_kernel(const uint32_t* __restrict__ lab,
                                                        const uint8_t* __restrict__ lvl, size_t n, uint32_t level,
                                                        const uint32_t* __restrict__ rep, uint32_t colour_base,
-                                                       uint64_t* __restrict__ out) {
+                                                       O* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint32_t v = 0;
@@ -503,7 +504,13 @@ static unsigned stream_grid(size_t n) {
 
 cudaError_t launch_snapshot(const uint32_t* lab, const uint8_t* lvl, size_t n_px, uint32_t level,
                             const uint32_t* rep, uint32_t colour_base, uint64_t* out, cudaStream_t s) {
-  snapshot_kernel<<<stream_grid(n_px), 256, 0, s>>>(lab, lvl, n_px, level, rep, colour_base, out);
+  snapshot_kernel<uint64_t><<<stream_grid(n_px), 256, 0, s>>>(lab, lvl, n_px, level, rep, colour_base, out);
+  return cudaGetLastError();
+}
+// the same as 32-bit words (pageable destinations: half the bytes on the link, widened by the host's workers)
+cudaError_t launch_snapshot32(const uint32_t* lab, const uint8_t* lvl, size_t n_px, uint32_t level,
+                              const uint32_t* rep, uint32_t colour_base, uint32_t* out, cudaStream_t s) {
+  snapshot_kernel<uint32_t><<<stream_grid(n_px), 256, 0, s>>>(lab, lvl, n_px, level, rep, colour_base, out);
   return cudaGetLastError();
 }
 

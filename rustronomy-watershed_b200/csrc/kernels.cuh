@@ -196,6 +196,8 @@ cudaError_t launch_forest_lake_counts(const uint32_t* ndistinct, ForestBuffers f
 // out[p] = lvl[p] <= level ? label : 0, label optionally mapped through rep[] (merging)
 cudaError_t launch_snapshot(const uint32_t* lab, const uint8_t* lvl, size_t n_px, uint32_t level,
                             const uint32_t* rep, uint32_t colour_base, uint64_t* out, cudaStream_t s);
+cudaError_t launch_snapshot32(const uint32_t* lab, const uint8_t* lvl, size_t n_px, uint32_t level,
+                              const uint32_t* rep, uint32_t colour_base, uint32_t* out, cudaStream_t s);
 cudaError_t launch_widen_labels(const uint32_t* lab, size_t n_px, uint64_t* out, cudaStream_t s);
 cudaError_t launch_strip_labels(const uint32_t* lab, size_t n_px, uint32_t* out, cudaStream_t s);
 // lvl_hist[b][256]: pixels coloured at each level (255 = never)
