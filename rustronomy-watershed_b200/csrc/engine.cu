@@ -1459,29 +1459,9 @@ ws_status host_run(ws_ctx* ctx, const ws_config* cfg, const ws_image* img, const
   return host_run_batch(ctx, cfg, nullptr, img, 1, img->rows, img->cols, seeds_rc, nullptr, nseeds, hr);
 }
 
-// Per-level snapshots streamed to the host: kernel into one of two device buffers on the
-// compute stream, device->host copy on the copy stream, double buffered.  `sink` receives
-// (level, host pointer valid until the next but one call) -- or the copy goes straight to
-// `direct` + level * npx when that is given.
-// host copy with several threads (one core moves ~10 GB/s, the D2H link ~55 GB/s)
-static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-  const unsigned hw = std::thread::hardware_concurrency();
-  const size_t nt = std::max<size_t>(1, std::min<size_t>(16, std::min<size_t>(hw ? hw : 1, bytes >> 22)));
-  if (nt == 1) {
-    memcpy(dst, src, bytes);
-    return;
-  }
-  std::vector<std::thread> th;
-  const size_t chunk = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
-  for (size_t t = 0; t < nt; ++t) {
-    const size_t lo = t * chunk;
-    if (lo >= bytes) break;
-    const size_t n = std::min(chunk, bytes - lo);
-    th.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, n); });
-  }
-  for (auto& t : th) t.join();
-}
-
+// Per-level snapshots streamed to the host, one level being cut on the device while the previous one crosses the
+// link.  `sink` receives (level, host pointer valid during the call) -- or the snapshots go to `direct` + level * npx
+// when that is given.
 template <typename Sink>
 ws_status stream_snapshots(ws_ctx* ctx, HostRun& hr, const ws_config* cfg, uint64_t* direct, Sink sink) {
   ws_plan* p = hr.plan;
